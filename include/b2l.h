@@ -1,0 +1,229 @@
+/*
+ * b2l.h - C ABI of libb200llama.so: the B200 (sm_100a) quantized-decode path for
+ * Lightning-AI/lit-llama.
+ *
+ * The reference has no native boundary of its own: its "operator API" for this path
+ * is a set of Python nn.Module classes that lit_llama/utils.py:141-162 swaps in for
+ * torch.nn.Linear, plus the model-level modules of lit_llama/model.py.  Each entry
+ * point below states the reference forward it replaces (file:line relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller (PyTorch).  The library
+ *    never allocates or frees device memory on the call path and never synchronises;
+ *    every call only enqueues work on `stream` and is CUDA-graph capturable.
+ *  - Return value: 0 = ok, <0 = bad argument / unsupported shape (B2L_E_*),
+ *    >0 = a cudaError_t.  b2l_last_error() returns a thread-local message.
+ *  - There is no CPU fallback.
+ *  - Activations are bf16 (B2L_BF16).  Scales/zeros may be bf16 or f32 (the
+ *    reference creates them in the default dtype, quantization.py:360-369).
+ */
+#ifndef B2L_H_
+#define B2L_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* b2l_stream_t; /* == cudaStream_t */
+
+enum { B2L_BF16 = 0, B2L_F32 = 1 };
+
+enum {
+  B2L_E_ARG = -1,         /* null pointer / negative size / misaligned pointer      */
+  B2L_E_UNSUPPORTED = -2, /* shape or mode outside what the kernels implement        */
+  B2L_E_STATE = -3        /* call sequence error (e.g. model not finalised)          */
+};
+
+int b2l_version(void);
+const char* b2l_last_error(void);
+/* Device facts the host side sizes grids with (SM count etc.).  0 on success. */
+int b2l_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------
+ * ColBlockQuantizedLinear  (lit_llama/quantization.py:340-423)
+ *
+ * Reference storage (quantization.py:350-369, 386-390): quant_weight is uint8, logical
+ * (out, in/epb) with strides (1, out) - i.e. memory is row-major (in/epb, out) - and
+ * entry nr of byte [o, j] holds column epb*j+nr at bit nr*bits.  scales/zeros are
+ * (out, n_groups) row-major, n_groups = ceil(in / tile_cols).
+ * ---------------------------------------------------------------------------- */
+
+/* get_weight(): dense (out, in) row-major weight, (level - zero) * scale evaluated in
+ * out_dtype like quantization.py:392-411 (bit-exact with the reference). */
+int b2l_q_dequant(const void* qw, const void* scales, const void* zeros, int sz_dtype,
+                  void* w_out, int out_dtype, int out_features, int in_features, int bits,
+                  int tile_cols, b2l_stream_t stream);
+
+/* forward(): y[M,N] = x[M,K] @ dequant(W)^T (+ bias).  Generic kernel: any bits in
+ * {4,8}, any tile_cols, any M; reads the reference layout directly.  Replaces both
+ * branches of quantization.py:413-423 (the Triton kernel :187-333 and the dense
+ * fallback).  x, y bf16 row-major with leading dimensions ldx, ldy (elements). */
+int b2l_q_linear(const void* x, int ldx, const void* qw, const void* scales, const void* zeros,
+                 int sz_dtype, const void* bias, void* y, int ldy, int M, int N, int K, int bits,
+                 int tile_cols, b2l_stream_t stream);
+
+/* One-time (load-time) re-tiling of a 4-bit, one-group-per-row weight for the
+ * tcgen05 kernel: [N/128 tiles][K/32 slabs][128 rows][16 B].  N is padded up to a
+ * multiple of 128 with zero levels.  Pure permutation of nibbles (bit-exact,
+ * invertible: b2l_q4_untile).  Precedent for load-time transforms in the
+ * reference: Linear8bitLt._load_from_state_dict, quantization.py:52-67. */
+size_t b2l_q4_tiled_bytes(int N, int K);
+int b2l_q4_tile(const void* qw, void* qw_tiled, int N, int K, b2l_stream_t stream);
+int b2l_q4_untile(const void* qw_tiled, void* qw, int N, int K, b2l_stream_t stream);
+
+/* Prologue / epilogue selectors of the fused tcgen05 linear. */
+enum { B2L_PRO_NONE = 0, B2L_PRO_RMSNORM = 1 };
+enum {
+  B2L_EPI_STORE = 0,    /* y = bf16(acc)                                              */
+  B2L_EPI_RESIDUAL = 1, /* y = bf16(bf16(acc) + res)            model.py:166-167       */
+  B2L_EPI_SWIGLU = 2    /* rows interleaved [64 of c_fc1 | 64 of c_fc2] per tile:
+                           y = bf16(bf16(silu(bf16(a))) * bf16(b))   model.py:252     */
+};
+
+typedef struct b2l_q4_linear_args {
+  const void* x;        /* bf16 [M, K], leading dim ldx                               */
+  int ldx;
+  const void* qw_tiled; /* from b2l_q4_tile                                           */
+  const void* scales;   /* [N] per-row                                                */
+  const void* zeros;    /* [N]                                                        */
+  int sz_dtype;
+  void* y;              /* bf16 [M, N_out], leading dim ldy (N_out = N/2 for SWIGLU)  */
+  int ldy;
+  int M, N, K;          /* M <= 16; N % 128 == 0 after padding; K % 32 == 0           */
+  int prologue;         /* B2L_PRO_*                                                  */
+  const void* norm_scale; /* bf16 [K] RMSNorm scale when prologue == RMSNORM          */
+  float eps;
+  int epilogue;         /* B2L_EPI_*                                                  */
+  const void* res;      /* bf16 [M, N] residual (leading dim ldres) for RESIDUAL      */
+  int ldres;
+  int split_k;          /* cluster size along K: 1,2,4,8 (0 = library picks)          */
+  int flags;            /* B2L_F_*                                                    */
+} b2l_q4_linear_args;
+
+enum {
+  B2L_F_PDL = 1,        /* launch with programmatic dependent launch                   */
+  B2L_F_ALIAS_N = 2,    /* B operand rows 8..15 alias rows 0..7 (M <= 8)               */
+  B2L_F_ROPE_ROWS = 4   /* b2l_attention: `rope` holds the T rows already selected by
+                           input_pos (the reference's call convention, model.py:93)    */
+};
+
+/* Fused [RMSNorm ->] int4 linear [-> residual | SwiGLU] on tcgen05.  Replaces
+ * RMSNorm.forward (model.py:270-277) + ColBlockQuantizedLinear.forward
+ * (quantization.py:413-423) + the residual add / silu*mul of Block/MLP.forward
+ * (model.py:166-167, 252). */
+int b2l_q4_linear_tc(const b2l_q4_linear_args* args, b2l_stream_t stream);
+
+/* ------------------------------------------------------------------------------
+ * model.py element-wise pieces (used by the module-level drop-ins and by prefill)
+ * ---------------------------------------------------------------------------- */
+
+/* RMSNorm.forward, model.py:270-277, evaluated with the reference's bf16 rounding
+ * points.  x, y bf16 [rows, C]. */
+int b2l_rmsnorm(const void* x, const void* scale, void* y, int rows, int C, float eps,
+                b2l_stream_t stream);
+
+/* transformer.wte(idx), model.py:102.  idx int32 or int64 [n]; out bf16 [n, C]. */
+int b2l_embedding(const void* idx, int idx_is_i64, const void* wte, void* out, int n, int C,
+                  int vocab, b2l_stream_t stream);
+
+/* silu(a) * b with the reference's bf16 rounding points, model.py:252. */
+int b2l_silu_mul(const void* a, const void* b, void* y, size_t n, b2l_stream_t stream);
+
+/* x + h, model.py:166-167. */
+int b2l_add(const void* a, const void* b, void* y, size_t n, b2l_stream_t stream);
+
+/* ------------------------------------------------------------------------------
+ * CausalSelfAttention.forward without the two linears, model.py:197-232:
+ * split qkv, apply_rope(q), apply_rope(k) (model.py:306-323), append k,v to the
+ * cache at input_pos (roll-when-full branch model.py:214-218 handled on the device
+ * with a ring offset), causal softmax(q k^T / sqrt(hs)) v.
+ *
+ * qkv   bf16 [B, T, 3*C]   (q | k | v thirds, each [nh, hs])
+ * k/v cache bf16 [B, nh, S, hs]; physical slot = (logical slot + *ring_start) % S
+ * rope  f32 [block_size, hs/2, 2] (cos, sin) - build_rope_cache, model.py:280-303
+ * input_pos int64 [T] on the device (never read by the host).  Query t writes its
+ *            k,v at logical slot min(input_pos[t], S-1) and attends slots <= that.
+ * ring_start int32 [1] on the device, read-only here; b2l_ring_advance moves it
+ * y     bf16 [B, T, C]
+ * work  f32 scratch of b2l_attn_workspace_bytes(...) for split-S partials
+ * ---------------------------------------------------------------------------- */
+size_t b2l_attn_workspace_bytes(int B, int n_head, int head_size, int T, int S);
+int b2l_attention(void* qkv, void* k_cache, void* v_cache, const void* rope,
+                  const int64_t* input_pos, const int32_t* ring_start, void* y, void* work, int B,
+                  int T, int n_head, int head_size, int S, int block_size, int flags,
+                  b2l_stream_t stream);
+
+/* The roll branch of model.py:214-218 as a ring: if input_pos[T-1] >= S the ring start
+ * advances by one slot (the oldest entry is dropped, exactly what torch.roll(-1) +
+ * overwrite of slot S-1 does).  Call once per forward, before the layers. */
+int b2l_ring_advance(const int64_t* input_pos, int T, int32_t* ring_start, int S,
+                     b2l_stream_t stream);
+
+/* Same without a cache (input_pos is None, model.py:104-106): positions 0..T-1.
+ * qkv is rotated in place; work as for b2l_attention with S = T. */
+int b2l_attention_nocache(void* qkv, const void* rope, void* y, void* work, int B, int T,
+                          int n_head, int head_size, int block_size, b2l_stream_t stream);
+
+/* kv_caches as the reference would hold them (logical order): un-rotates the ring
+ * into `out` [B, nh, S, hs]. */
+int b2l_kv_unroll(const void* cache, const int32_t* ring_start, void* out, int B, int n_head,
+                  int S, int head_size, b2l_stream_t stream);
+
+/* ------------------------------------------------------------------------------
+ * Whole decode step: LLaMA.forward for T == 1 with a KV cache (model.py:76-122),
+ * every kernel of the step enqueued by one call.
+ * ---------------------------------------------------------------------------- */
+typedef struct b2l_q4_weight {
+  const void* qw_tiled;
+  const void* scales;
+  const void* zeros;
+  int N, K;
+} b2l_q4_weight;
+
+typedef struct b2l_layer {
+  const void* rms_1;       /* bf16 [C] */
+  const void* rms_2;       /* bf16 [C] */
+  b2l_q4_weight c_attn;    /* [3C, C]                                                */
+  b2l_q4_weight c_proj;    /* [C, C]                                                 */
+  b2l_q4_weight c_fc12;    /* [2*n_hidden, C], rows interleaved 64/64 per tile       */
+  b2l_q4_weight mlp_proj;  /* [C, n_hidden]                                          */
+  void* k_cache;           /* bf16 [B, nh, S, hs]                                    */
+  void* v_cache;
+} b2l_layer;
+
+typedef struct b2l_decode_args {
+  int n_layer, n_head, n_embd, n_hidden, vocab; /* vocab = padded_vocab_size          */
+  int B, S;                                     /* batch, max_seq_length              */
+  int sz_dtype;
+  float eps;
+  const b2l_layer* layers;   /* HOST array [n_layer]                                  */
+  const void* wte;           /* bf16 [vocab, C]                                       */
+  const void* ln_f;          /* bf16 [C]                                              */
+  b2l_q4_weight lm_head;     /* [vocab, C]                                            */
+  const void* rope;          /* f32 [block_size, hs/2, 2]                             */
+  const void* idx;           /* int32/int64 [B] tokens of this step                   */
+  int idx_is_i64;
+  const int64_t* input_pos;  /* int64 [1]                                             */
+  int32_t* ring_start;       /* int32 [1]; advanced by the step when the cache is full */
+  int block_size;            /* rows of the rope table                                */
+  void* x;                   /* bf16 [B, C]   residual stream scratch                 */
+  void* qkv;                 /* bf16 [B, 3C]                                          */
+  void* att;                 /* bf16 [B, C]                                           */
+  void* hid;                 /* bf16 [B, n_hidden]                                    */
+  void* attn_work;           /* f32, b2l_attn_workspace_bytes                         */
+  void* logits;              /* bf16 [B, vocab]                                       */
+  int flags;                 /* B2L_F_*                                               */
+} b2l_decode_args;
+
+int b2l_decode_step(const b2l_decode_args* args, b2l_stream_t stream);
+/* Number of kernels one b2l_decode_step enqueues (for bench.py's gpu_launches). */
+int b2l_decode_step_launches(const b2l_decode_args* args);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2L_H_ */

@@ -1,0 +1,114 @@
+// Error state, device facts and the whole-token entry point of libb200llama.
+#include <mutex>
+
+#include "b2l_common.cuh"
+
+namespace b2l {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  (void)cudaGetLastError();  // clear the sticky-less error so the next call starts clean
+  return (int)e;
+}
+
+int sm_count() {
+  static int n = 0;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  });
+  return n;
+}
+
+}  // namespace b2l
+
+using namespace b2l;
+
+extern "C" int b2l_version(void) { return 100; }
+
+extern "C" const char* b2l_last_error(void) { return g_err; }
+
+extern "C" int b2l_device_info(int* sm, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  B2L_CUDA(cudaGetDevice(&dev));
+  int a = 0, b = 0, c = 0;
+  B2L_CUDA(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev));
+  B2L_CUDA(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev));
+  B2L_CUDA(cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm) *sm = a;
+  if (cc_major) *cc_major = b;
+  if (cc_minor) *cc_minor = c;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// LLaMA.forward for one new token per sequence (model.py:76-122 with T == 1):
+//   wte -> n_layer x Block (model.py:156-168) -> ln_f -> lm_head
+// Per Block: [rms_1 + c_attn] -> rope/append/attention -> [c_proj + residual]
+//            -> [rms_2 + c_fc1|c_fc2 + silu*mul] -> [mlp.c_proj + residual]
+// ---------------------------------------------------------------------------------
+static int q4_call(const b2l_q4_weight& w, const void* x, int ldx, void* y, int ldy, int M, int sz_dtype, int prologue,
+                   const void* norm_scale, float eps, int epilogue, const void* res, int ldres, int flags,
+                   b2l_stream_t stream) {
+  b2l_q4_linear_args a{};
+  a.x = x; a.ldx = ldx;
+  a.qw_tiled = w.qw_tiled; a.scales = w.scales; a.zeros = w.zeros; a.sz_dtype = sz_dtype;
+  a.y = y; a.ldy = ldy;
+  a.M = M; a.N = w.N; a.K = w.K;
+  a.prologue = prologue; a.norm_scale = norm_scale; a.eps = eps;
+  a.epilogue = epilogue; a.res = res; a.ldres = ldres;
+  a.split_k = 0;
+  a.flags = flags;
+  return b2l_q4_linear_tc(&a, stream);
+}
+
+extern "C" int b2l_decode_step_launches(const b2l_decode_args* d) {
+  if (!d) return 0;
+  return 2 + d->n_layer * 7 + 1;  // embedding + ring advance, 7 per Block, ln_f+lm_head
+}
+
+extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {
+  B2L_CHECK_ARG(d != nullptr && d->layers != nullptr, "b2l_decode_step: null args");
+  B2L_CHECK_ARG(d->n_layer > 0 && d->n_head > 0 && d->n_embd % d->n_head == 0 && d->B >= 1 && d->S >= 1,
+                "b2l_decode_step: bad model shape");
+  B2L_CHECK_SUPPORTED(d->B <= 16, "b2l_decode_step: batch %d > 16", d->B);
+  B2L_CHECK_ARG(d->wte && d->ln_f && d->rope && d->idx && d->input_pos && d->ring_start && d->x && d->qkv && d->att &&
+                    d->hid && d->attn_work && d->logits,
+                "b2l_decode_step: null pointer");
+  const int C = d->n_embd, hs = C / d->n_head, B = d->B;
+  const int fl = d->flags;
+  int rc;
+  if ((rc = b2l_ring_advance(d->input_pos, 1, d->ring_start, d->S, stream))) return rc;
+  if ((rc = b2l_embedding(d->idx, d->idx_is_i64, d->wte, d->x, B, C, d->vocab, stream))) return rc;
+  for (int l = 0; l < d->n_layer; ++l) {
+    const b2l_layer& L = d->layers[l];
+    if ((rc = q4_call(L.c_attn, d->x, C, d->qkv, 3 * C, B, d->sz_dtype, B2L_PRO_RMSNORM, L.rms_1, d->eps, B2L_EPI_STORE,
+                      nullptr, 0, fl, stream)))
+      return rc;
+    if ((rc = b2l_attention(d->qkv, L.k_cache, L.v_cache, d->rope, d->input_pos, d->ring_start, d->att, d->attn_work, B,
+                            1, d->n_head, hs, d->S, d->block_size, fl, stream)))
+      return rc;
+    if ((rc = q4_call(L.c_proj, d->att, C, d->x, C, B, d->sz_dtype, B2L_PRO_NONE, nullptr, 0.f, B2L_EPI_RESIDUAL, d->x, C,
+                      fl, stream)))
+      return rc;
+    if ((rc = q4_call(L.c_fc12, d->x, C, d->hid, d->n_hidden, B, d->sz_dtype, B2L_PRO_RMSNORM, L.rms_2, d->eps,
+                      B2L_EPI_SWIGLU, nullptr, 0, fl, stream)))
+      return rc;
+    if ((rc = q4_call(L.mlp_proj, d->hid, d->n_hidden, d->x, C, B, d->sz_dtype, B2L_PRO_NONE, nullptr, 0.f,
+                      B2L_EPI_RESIDUAL, d->x, C, fl, stream)))
+      return rc;
+  }
+  return q4_call(d->lm_head, d->x, C, d->logits, d->vocab, B, d->sz_dtype, B2L_PRO_RMSNORM, d->ln_f, d->eps,
+                 B2L_EPI_STORE, nullptr, 0, fl, stream);
+}

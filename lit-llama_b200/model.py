@@ -1,0 +1,482 @@
+"""Drop-in LLaMA modules (reference: lit_llama/model.py) backed by libb200llama.
+
+Same classes, constructor signatures, parameter/buffer names and forward signatures as
+the reference, so `with quantization(mode): model = LLaMA.from_name(name)` followed by
+`model.load_state_dict(checkpoint)` and the reference's `generate()` work unchanged.
+Every forward runs hand-written sm_100a kernels (include/b2l.h); tensors must be CUDA
+bf16 - there is no CPU fallback.
+
+Two execution paths behind `LLaMA.forward`:
+  * decode (T == 1 with a KV cache, every Linear a tcgen05-capable gptq.int4 layer):
+    one C call enqueues the whole token (`b2l_decode_step`), replayed as a CUDA graph.
+  * everything else (prefill, no-cache forward, other Linear kinds): module by module.
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+from typing_extensions import Self
+
+from . import _lib as L
+from .utils import find_multiple
+
+MaskCache = torch.Tensor
+RoPECache = torch.Tensor
+KVCache = Tuple[torch.Tensor, torch.Tensor]
+
+
+@dataclass
+class LLaMAConfig:
+    """model.py:25-40."""
+    block_size: int = 2048
+    vocab_size: int = 32000
+    padded_vocab_size: Optional[int] = None
+    n_layer: int = 32
+    n_head: int = 32
+    n_embd: int = 4096
+
+    def __post_init__(self):
+        if self.padded_vocab_size is None:
+            self.padded_vocab_size = find_multiple(self.vocab_size, 64)
+
+    @classmethod
+    def from_name(cls, name: str) -> Self:
+        return cls(**llama_configs[name])
+
+
+llama_configs = {  # model.py:43-48
+    "7B": dict(n_layer=32, n_head=32, n_embd=4096),
+    "13B": dict(n_layer=40, n_head=40, n_embd=5120),
+    "30B": dict(n_layer=60, n_head=52, n_embd=6656),
+    "65B": dict(n_layer=80, n_head=64, n_embd=8192),
+}
+
+
+def _linear(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    return module(x)
+
+
+class RMSNorm(nn.Module):
+    """model.py:257-277; the kernel keeps the reference's bf16 rounding points."""
+
+    def __init__(self, size: int, dim: int = -1, eps: float = 1e-5) -> None:
+        super().__init__()
+        self.scale = nn.Parameter(torch.ones(size))
+        self.eps = eps
+        self.dim = dim
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        L.require_cuda_bf16(x, "RMSNorm.forward")
+        if self.dim not in (-1, x.dim() - 1):
+            raise RuntimeError("RMSNorm: only dim=-1 is implemented")
+        xc = x.contiguous()
+        C_ = xc.shape[-1]
+        y = torch.empty_like(xc)
+        scale = self.scale if self.scale.dtype == torch.bfloat16 else self.scale.to(torch.bfloat16)
+        rc = L.lib().b2l_rmsnorm(xc.data_ptr(), scale.data_ptr(), y.data_ptr(), xc.numel() // C_, C_, float(self.eps), L.stream_ptr())
+        L.check(rc, "b2l_rmsnorm")
+        return y
+
+
+def build_rope_cache(seq_len: int, n_elem: int, dtype: torch.dtype, device: torch.device, base: int = 10000) -> RoPECache:
+    """model.py:280-303.  Table construction is one-time host-side setup (torch ops)."""
+    theta = 1.0 / (base ** (torch.arange(0, n_elem, 2, dtype=dtype, device=device) / n_elem))
+    seq_idx = torch.arange(seq_len, dtype=dtype, device=device)
+    idx_theta = torch.outer(seq_idx, theta).float()
+    cache = torch.stack([torch.cos(idx_theta), torch.sin(idx_theta)], dim=-1)
+    if dtype in (torch.float16, torch.bfloat16, torch.int8):
+        cache = cache.half()
+    return cache
+
+
+def apply_rope(x: torch.Tensor, rope_cache: RoPECache) -> torch.Tensor:
+    """model.py:306-323 as a stand-alone op: x (B, T, n_head, hs) -> rotated copy.
+    (Inside the model the rotation is fused with the KV append, see b2l_attention.)"""
+    L.require_cuda_bf16(x, "apply_rope")
+    B, T, nh, hs = x.shape
+    qkv = torch.zeros((B, T, 3, nh, hs), device=x.device, dtype=x.dtype)
+    qkv[:, :, 0] = x
+    rows = rope_cache[:T].float().contiguous()
+    y = torch.empty((B, T, nh * hs), device=x.device, dtype=x.dtype)
+    work = torch.empty(L.lib().b2l_attn_workspace_bytes(B, nh, hs, T, T) // 4 + 1, device=x.device, dtype=torch.float32)
+    rc = L.lib().b2l_attention_nocache(qkv.data_ptr(), rows.data_ptr(), y.data_ptr(), work.data_ptr(), B, T, nh, hs, T, L.stream_ptr())
+    L.check(rc, "b2l_attention_nocache")
+    return qkv[:, :, 0].contiguous()
+
+
+class CausalSelfAttention(nn.Module):
+    """model.py:171-237."""
+
+    def __init__(self, config: LLaMAConfig) -> None:
+        super().__init__()
+        assert config.n_embd % config.n_head == 0
+        self.c_attn = nn.Linear(config.n_embd, 3 * config.n_embd, bias=False)
+        self.c_proj = nn.Linear(config.n_embd, config.n_embd, bias=False)
+        self.n_head = config.n_head
+        self.n_embd = config.n_embd
+        self.block_size = config.block_size
+        self._ring: Optional[torch.Tensor] = None  # shared by LLaMA; private when used stand-alone
+        self._ring_shared = False
+
+    def forward(
+        self,
+        x: torch.Tensor,
+        rope: RoPECache,
+        mask: MaskCache,
+        max_seq_length: int,
+        input_pos: Optional[torch.Tensor] = None,
+        kv_cache: Optional[KVCache] = None,
+        *,
+        _rope_is_table: bool = False,
+    ) -> Tuple[torch.Tensor, Optional[KVCache]]:
+        """`mask` is accepted for signature parity and ignored: the kernel derives the
+        causal mask from input_pos exactly as model.py:94-96 builds it from tril."""
+        L.require_cuda_bf16(x, "CausalSelfAttention.forward")
+        B, T, C_ = x.size()
+        hs = C_ // self.n_head
+        qkv = self.c_attn(x)
+        if not qkv.is_contiguous():
+            qkv = qkv.contiguous()
+        y = torch.empty((B, T, C_), device=x.device, dtype=x.dtype)
+        lib = L.lib()
+        rope32 = rope if rope.dtype == torch.float32 else rope.float()
+        rope32 = rope32.contiguous()
+        if kv_cache is None:
+            work = torch.empty(lib.b2l_attn_workspace_bytes(B, self.n_head, hs, T, T) // 4 + 1, device=x.device, dtype=torch.float32)
+            rows = rope32 if not _rope_is_table else rope32[:T]
+            rc = lib.b2l_attention_nocache(qkv.data_ptr(), rows.data_ptr(), y.data_ptr(), work.data_ptr(), B, T,
+                                           self.n_head, hs, rows.shape[0], L.stream_ptr())
+            L.check(rc, "b2l_attention_nocache")
+        else:
+            cache_k, cache_v = kv_cache
+            S = cache_k.shape[2]
+            assert S == max_seq_length and cache_k.is_contiguous() and cache_v.is_contiguous()
+            pos = input_pos.reshape(-1).to(torch.int64)
+            if self._ring is None or self._ring.device != x.device:
+                self._ring = torch.zeros(1, dtype=torch.int32, device=x.device)
+            if not self._ring_shared:  # stand-alone use: this module owns the roll state (model.py:214-218)
+                L.check(lib.b2l_ring_advance(pos.data_ptr(), T, self._ring.data_ptr(), S, L.stream_ptr()), "b2l_ring_advance")
+            work = torch.empty(lib.b2l_attn_workspace_bytes(B, self.n_head, hs, T, S) // 4 + 1, device=x.device, dtype=torch.float32)
+            flags = 0 if _rope_is_table else 4  # B2L_F_ROPE_ROWS
+            rc = lib.b2l_attention(qkv.data_ptr(), cache_k.data_ptr(), cache_v.data_ptr(), rope32.data_ptr(), pos.data_ptr(),
+                                   self._ring.data_ptr(), y.data_ptr(), work.data_ptr(), B, T, self.n_head, hs, S,
+                                   rope32.shape[0], flags, L.stream_ptr())
+            L.check(rc, "b2l_attention")
+        y = self.c_proj(y)
+        return y, kv_cache
+
+
+class MLP(nn.Module):
+    """model.py:240-254."""
+
+    def __init__(self, config: LLaMAConfig) -> None:
+        super().__init__()
+        hidden_dim = 4 * config.n_embd
+        n_hidden = int(2 * hidden_dim / 3)
+        n_hidden = find_multiple(n_hidden, 256)
+        self.c_fc1 = nn.Linear(config.n_embd, n_hidden, bias=False)
+        self.c_fc2 = nn.Linear(config.n_embd, n_hidden, bias=False)
+        self.c_proj = nn.Linear(n_hidden, config.n_embd, bias=False)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        L.require_cuda_bf16(x, "MLP.forward")
+        a = self.c_fc1(x).contiguous()
+        b = self.c_fc2(x).contiguous()
+        h = torch.empty_like(a)
+        L.check(L.lib().b2l_silu_mul(a.data_ptr(), b.data_ptr(), h.data_ptr(), a.numel(), L.stream_ptr()), "b2l_silu_mul")
+        return self.c_proj(h)
+
+
+def _add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    a, b = a.contiguous(), b.contiguous()
+    y = torch.empty_like(a)
+    L.check(L.lib().b2l_add(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), L.stream_ptr()), "b2l_add")
+    return y
+
+
+class Block(nn.Module):
+    """model.py:148-168."""
+
+    def __init__(self, config: LLaMAConfig) -> None:
+        super().__init__()
+        self.rms_1 = RMSNorm(config.n_embd)
+        self.attn = CausalSelfAttention(config)
+        self.rms_2 = RMSNorm(config.n_embd)
+        self.mlp = MLP(config)
+
+    def forward(
+        self,
+        x: torch.Tensor,
+        rope: RoPECache,
+        mask: MaskCache,
+        max_seq_length: int,
+        input_pos: Optional[torch.Tensor] = None,
+        kv_cache: Optional[KVCache] = None,
+        **kw,
+    ) -> Tuple[torch.Tensor, Optional[KVCache]]:
+        h, new_kv_cache = self.attn(self.rms_1(x), rope, mask, max_seq_length, input_pos, kv_cache, **kw)
+        x = _add(x, h)
+        x = _add(x, self.mlp(self.rms_2(x)))
+        return x, new_kv_cache
+
+
+class _DecodeState:
+    """Static buffers + the C argument block of b2l_decode_step for one (B, S)."""
+
+    def __init__(self, model: "LLaMA", B: int, S: int, device: torch.device, idx_dtype: torch.dtype) -> None:
+        from .quantization import ColBlockQuantizedLinear
+
+        cfg = model.config
+        C_, nh = cfg.n_embd, cfg.n_head
+        hs = C_ // nh
+        bf = dict(device=device, dtype=torch.bfloat16)
+        self.B, self.S = B, S
+        self.idx = torch.zeros(B, dtype=idx_dtype, device=device)
+        self.pos = torch.zeros(1, dtype=torch.int64, device=device)
+        self.x = torch.empty((B, C_), **bf)
+        self.qkv = torch.empty((B, 3 * C_), **bf)
+        self.att = torch.empty((B, C_), **bf)
+        n_hidden = model.transformer.h[0].mlp.c_fc1.out_features
+        self.hid = torch.empty((B, n_hidden), **bf)
+        self.logits = torch.empty((B, 1, cfg.padded_vocab_size), **bf)
+        lib = L.lib()
+        self.work = torch.empty(lib.b2l_attn_workspace_bytes(B, nh, hs, 1, S) // 4 + 1, device=device, dtype=torch.float32)
+        self.keep = []  # tensors the argument block points into
+
+        def q4(lin: ColBlockQuantizedLinear) -> L.Q4Weight:
+            t = lin.tiled()
+            return L.Q4Weight(t.data_ptr(), lin.scales.data_ptr(), lin.zeros.data_ptr(), lin.out_features, lin.in_features)
+
+        def bf16(p: torch.Tensor) -> torch.Tensor:
+            t = p.detach()
+            if t.dtype != torch.bfloat16:
+                t = t.to(torch.bfloat16)
+                self.keep.append(t)
+            return t
+
+        layers = (L.Layer * cfg.n_layer)()
+        for i, blk in enumerate(model.transformer.h):
+            fc12 = model._fc12(i)
+            k, v = model.kv_caches[i]
+            layers[i] = L.Layer(
+                rms_1=bf16(blk.rms_1.scale).data_ptr(), rms_2=bf16(blk.rms_2.scale).data_ptr(),
+                c_attn=q4(blk.attn.c_attn), c_proj=q4(blk.attn.c_proj),
+                c_fc12=L.Q4Weight(fc12[0].data_ptr(), fc12[1].data_ptr(), fc12[2].data_ptr(), 2 * n_hidden, C_),
+                mlp_proj=q4(blk.mlp.c_proj), k_cache=k.data_ptr(), v_cache=v.data_ptr())
+        self.layers = layers
+        lin0 = model.lm_head
+        self.args = L.DecodeArgs(
+            n_layer=cfg.n_layer, n_head=nh, n_embd=C_, n_hidden=n_hidden, vocab=cfg.padded_vocab_size, B=B, S=S,
+            sz_dtype=L.sz_dtype_of(lin0.scales), eps=float(model.transformer.ln_f.eps), layers=layers,
+            wte=bf16(model.transformer.wte.weight).data_ptr(), ln_f=bf16(model.transformer.ln_f.scale).data_ptr(),
+            lm_head=q4(lin0), rope=model.rope_cache.data_ptr(), idx=self.idx.data_ptr(),
+            idx_is_i64=1 if idx_dtype == torch.int64 else 0, input_pos=self.pos.data_ptr(),
+            ring_start=model._ring.data_ptr(), block_size=cfg.block_size, x=self.x.data_ptr(), qkv=self.qkv.data_ptr(),
+            att=self.att.data_ptr(), hid=self.hid.data_ptr(), attn_work=self.work.data_ptr(),
+            logits=self.logits.data_ptr(), flags=model.decode_flags)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.calls = 0
+
+    def enqueue(self) -> None:
+        L.check(L.lib().b2l_decode_step(C.byref(self.args), L.stream_ptr()), "b2l_decode_step")
+
+
+class LLaMA(nn.Module):
+    """model.py:51-145."""
+
+    #: replay the decode step as a CUDA graph after this many eager steps (0 = never)
+    graph_after: int = 2
+    #: flags passed to b2l_decode_step (1 = programmatic dependent launch)
+    decode_flags: int = 1
+    #: return a fresh logits tensor per call like the reference (False: a view of the static buffer)
+    copy_logits: bool = True
+
+    def __init__(self, config: LLaMAConfig) -> None:
+        super().__init__()
+        assert config.padded_vocab_size is not None
+        self.config = config
+
+        self.lm_head = nn.Linear(config.n_embd, config.padded_vocab_size, bias=False)
+        self.transformer = nn.ModuleDict(
+            dict(
+                wte=nn.Embedding(config.padded_vocab_size, config.n_embd),
+                h=nn.ModuleList(Block(config) for _ in range(config.n_layer)),
+                ln_f=RMSNorm(config.n_embd),
+            )
+        )
+
+        self.rope_cache: Optional[RoPECache] = None
+        self.mask_cache: Optional[MaskCache] = None  # kept for attribute parity; never materialised
+        self.kv_caches: List[KVCache] = []
+        self._ring: Optional[torch.Tensor] = None
+        self._kv_store: Optional[torch.Tensor] = None
+        self._decode: Optional[_DecodeState] = None
+        self._fast_ok: Optional[bool] = None  # every Linear is a tcgen05-capable int4 layer (checked once)
+        self._fc12_cache = {}
+
+    def _init_weights(self, module: nn.Module) -> None:
+        """model.py:70-74."""
+        if isinstance(module, nn.Linear) and hasattr(module, "weight"):
+            torch.nn.init.normal_(module.weight, mean=0.0, std=0.02 / math.sqrt(2 * self.config.n_layer))
+        elif isinstance(module, nn.Embedding):
+            torch.nn.init.normal_(module.weight, mean=0.0, std=0.02 / math.sqrt(2 * self.config.n_layer))
+
+    @classmethod
+    def from_name(cls, name: str) -> Self:
+        return cls(LLaMAConfig.from_name(name))
+
+    def build_rope_cache(self, idx: torch.Tensor) -> RoPECache:
+        """model.py:128-134: called with the integer token tensor, so the table is fp32."""
+        return build_rope_cache(seq_len=self.config.block_size, n_elem=self.config.n_embd // self.config.n_head,
+                                dtype=idx.dtype, device=idx.device)
+
+    def build_mask_cache(self, idx: torch.Tensor) -> MaskCache:
+        """model.py:136-138 (provided for parity; the kernels never read a mask tensor)."""
+        ones = torch.ones((self.config.block_size, self.config.block_size), device=idx.device, dtype=torch.bool)
+        return torch.tril(ones).unsqueeze(0).unsqueeze(0)
+
+    def reset_cache(self) -> None:
+        """model.py:140-145."""
+        self.kv_caches.clear()
+        self._kv_store = None
+        self._decode = None
+        if self._ring is not None:
+            self._ring.zero_()
+
+    # ------------------------------------------------------------------ helpers
+    def _fc12(self, i: int):
+        """c_fc1 and c_fc2 of layer i interleaved 64 rows / 64 rows per 128-row tile and
+        re-tiled, so one tcgen05 tile holds silu's argument and its multiplier."""
+        mlp = self.transformer.h[i].mlp
+        key = (mlp.c_fc1.quant_weight.data_ptr(), mlp.c_fc1.quant_weight._version,
+               mlp.c_fc2.quant_weight.data_ptr(), mlp.c_fc2.quant_weight._version)
+        hit = self._fc12_cache.get(i)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        nh, K = mlp.c_fc1.out_features, mlp.c_fc1.in_features
+        assert nh % 64 == 0
+
+        def inter(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:  # rows (dim 0) of a, b -> [t][64 a | 64 b]
+            return torch.stack((a.reshape(nh // 64, 64, *a.shape[1:]), b.reshape(nh // 64, 64, *b.shape[1:])), dim=1).reshape(2 * nh, *a.shape[1:])
+
+        qw = inter(mlp.c_fc1.quant_weight, mlp.c_fc2.quant_weight).t().contiguous().t()  # reference layout (1, 2nh)
+        scales = inter(mlp.c_fc1.scales, mlp.c_fc2.scales).contiguous()
+        zeros = inter(mlp.c_fc1.zeros, mlp.c_fc2.zeros).contiguous()
+        lib = L.lib()
+        tiled = torch.empty(lib.b2l_q4_tiled_bytes(2 * nh, K), dtype=torch.uint8, device=qw.device)
+        L.check(lib.b2l_q4_tile(qw.data_ptr(), tiled.data_ptr(), 2 * nh, K, L.stream_ptr()), "b2l_q4_tile")
+        val = (tiled, scales, zeros)
+        self._fc12_cache[i] = (key, val)
+        return val
+
+    def _fast_decode_ok(self) -> bool:
+        from .quantization import ColBlockQuantizedLinear
+
+        def ok(m):
+            return isinstance(m, ColBlockQuantizedLinear) and m.tc_capable
+
+        if not ok(self.lm_head) or self.config.n_embd % 8 != 0:
+            return False
+        dt = self.lm_head.scales.dtype
+        for blk in self.transformer.h:
+            lins = (blk.attn.c_attn, blk.attn.c_proj, blk.mlp.c_fc1, blk.mlp.c_fc2, blk.mlp.c_proj)
+            if not all(ok(m) and m.scales.dtype == dt for m in lins):
+                return False
+            if blk.mlp.c_fc1.out_features % 64 != 0:
+                return False
+        return True
+
+    def logical_kv_caches(self) -> List[KVCache]:
+        """kv_caches in the reference's slot order.  Identical to `kv_caches` until the
+        roll branch (model.py:214-218) has triggered; afterwards the physical tensors are
+        a ring and this returns the un-rotated copies the reference would hold."""
+        out = []
+        lib = L.lib()
+        for k, v in self.kv_caches:
+            B, nh, S, hs = k.shape
+            ko, vo = torch.empty_like(k), torch.empty_like(v)
+            L.check(lib.b2l_kv_unroll(k.data_ptr(), self._ring.data_ptr(), ko.data_ptr(), B, nh, S, hs, L.stream_ptr()), "b2l_kv_unroll")
+            L.check(lib.b2l_kv_unroll(v.data_ptr(), self._ring.data_ptr(), vo.data_ptr(), B, nh, S, hs, L.stream_ptr()), "b2l_kv_unroll")
+            out.append((ko, vo))
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def forward(
+        self, idx: torch.Tensor, max_seq_length: Optional[int] = None, input_pos: Optional[torch.Tensor] = None
+    ) -> Union[torch.Tensor, Tuple[torch.Tensor, List[KVCache]]]:
+        B, T = idx.size()
+        if not idx.is_cuda:
+            raise RuntimeError(f"LLaMA.forward: idx is on {idx.device}; lit_llama_b200 runs on CUDA only (no CPU fallback)")
+
+        block_size = self.config.block_size
+        if max_seq_length is None:
+            max_seq_length = block_size
+        assert T <= max_seq_length, f"Cannot forward sequence of length {T}, max seq length is only {max_seq_length}"
+        assert max_seq_length <= block_size, f"Cannot attend to {max_seq_length}, block size is only {block_size}"
+        assert T <= block_size, f"Cannot forward sequence of length {T}, block size is only {block_size}"
+
+        if self.rope_cache is None or self.rope_cache.device != idx.device:
+            self.rope_cache = self.build_rope_cache(idx).float().contiguous()
+        if self._ring is None or self._ring.device != idx.device:
+            self._ring = torch.zeros(1, dtype=torch.int32, device=idx.device)
+            for blk in self.transformer.h:
+                blk.attn._ring, blk.attn._ring_shared = self._ring, True
+
+        if input_pos is not None and not self.kv_caches:
+            cfg = self.config
+            hs = cfg.n_embd // cfg.n_head
+            self._kv_store = torch.zeros((cfg.n_layer, 2, B, cfg.n_head, max_seq_length, hs), device=idx.device, dtype=torch.bfloat16)
+            self.kv_caches = [(self._kv_store[i, 0], self._kv_store[i, 1]) for i in range(cfg.n_layer)]
+            self._decode = None
+
+        # ---- decode: one C call per token, replayed as a CUDA graph
+        st = None
+        if input_pos is not None and T == 1 and B <= 16 and idx.dtype in (torch.int32, torch.int64):
+            st = self._decode
+            if st is None or st.B != B or st.S != max_seq_length or st.idx.dtype != idx.dtype:
+                if self._fast_ok is None:
+                    self._fast_ok = self._fast_decode_ok()
+                st = self._decode = _DecodeState(self, B, max_seq_length, idx.device, idx.dtype) if self._fast_ok else None
+        if st is not None:
+            st.idx.copy_(idx.reshape(-1))
+            st.pos.copy_(input_pos.reshape(-1)[-1:])
+            if st.graph is not None:
+                st.graph.replay()
+            elif self.graph_after and st.calls >= self.graph_after:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st.enqueue()
+                st.graph = g
+                g.replay()
+            else:
+                st.enqueue()
+            st.calls += 1
+            return st.logits.clone() if self.copy_logits else st.logits
+
+        # ---- prefill / no-cache / non-int4 linears: module by module
+        x = torch.empty((B, T, self.config.n_embd), device=idx.device, dtype=torch.bfloat16)
+        wte = self.transformer.wte.weight
+        if wte.dtype != torch.bfloat16:
+            raise RuntimeError(f"wte dtype {wte.dtype} unsupported; the model must be bf16 (model.to(torch.bfloat16))")
+        idx_c = idx.contiguous()
+        if idx_c.dtype not in (torch.int32, torch.int64):
+            idx_c = idx_c.to(torch.int64)
+        rc = L.lib().b2l_embedding(idx_c.data_ptr(), 1 if idx_c.dtype == torch.int64 else 0, wte.data_ptr(), x.data_ptr(),
+                                   B * T, self.config.n_embd, wte.shape[0], L.stream_ptr())
+        L.check(rc, "b2l_embedding")
+
+        if input_pos is None:  # proxy for use_cache=False (model.py:104-106)
+            for block in self.transformer.h:
+                x, _ = block(x, self.rope_cache, None, max_seq_length, _rope_is_table=True)
+        else:
+            pos = input_pos.reshape(-1).to(torch.int64)
+            L.check(L.lib().b2l_ring_advance(pos.data_ptr(), T, self._ring.data_ptr(), max_seq_length, L.stream_ptr()), "b2l_ring_advance")
+            for i, block in enumerate(self.transformer.h):
+                x, self.kv_caches[i] = block(x, self.rope_cache, None, max_seq_length, pos, self.kv_caches[i], _rope_is_table=True)
+
+        x = self.transformer.ln_f(x)
+        logits = self.lm_head(x)  # (b, t, vocab_size)
+        return logits

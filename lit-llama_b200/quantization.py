@@ -1,0 +1,159 @@
+"""Drop-in quantized linears (reference: lit_llama/quantization.py).
+
+`ColBlockQuantizedLinear` keeps the reference's constructor, attributes, buffers
+(names, shapes, dtypes, strides) and `state_dict` keys (quantization.py:340-374), so a
+`llama-gptq.4bit.pth` produced by the reference's quantize/gptq.py loads unchanged.
+`forward` runs hand-written sm_100a kernels through the C ABI of include/b2l.h; there
+is no Triton, no dense fallback and no CPU path.
+"""
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+class ColBlockQuantizedLinear(torch.nn.Module):
+    """Weight-only int4 / int8 linear with per-row (or per column-group) scale and zero.
+
+    Same signature as the reference class (quantization.py:340-374).  Storage:
+    `quant_weight` uint8 (out, in/epb) with strides (1, out); entry nr of a byte holds
+    column epb*j+nr at bit nr*bits (quantization.py:386-390).  `scales`/`zeros`
+    (out, ceil(in/tile_cols)) in the default dtype; `bias` (out,) or None.
+    """
+
+    def __init__(self, in_features, out_features, bias: bool, *, bits, tile_cols):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.tile_cols = tile_cols if tile_cols != -1 else self.in_features
+        self.bits = bits
+        self.entries_per_byte = 8 // bits
+        assert self.entries_per_byte > 0 and self.entries_per_byte * self.bits == 8
+        assert in_features % self.entries_per_byte == 0
+        self.register_buffer(
+            "quant_weight",
+            torch.empty((self.out_features, self.in_features // self.entries_per_byte), dtype=torch.uint8).t().contiguous().t(),
+        )
+        n_groups = (self.in_features + self.tile_cols - 1) // self.tile_cols
+        self.register_buffer("scales", torch.empty((self.out_features, n_groups)))
+        self.register_buffer("zeros", torch.empty_like(self.scales))
+        assert isinstance(bias, bool)
+        if bias:
+            self.register_buffer("bias", torch.empty((self.out_features,)))
+        else:
+            self.register_buffer("bias", None)
+        self._tiled = None        # load-time re-tiling for the tcgen05 kernel (not part of state_dict)
+        self._tiled_key = None
+
+    # ------------------------------------------------------------------ packing (load-time, any device)
+    def pack_weight(self, weight):
+        """quantization.py:376-390: weight = scale * (level - zero) -> packed levels."""
+        weight = weight.to(device=self.quant_weight.device, copy=True)
+        for j in range(self.scales.size(1)):
+            sl = slice(j * self.tile_cols, (j + 1) * self.tile_cols)
+            weight[:, sl] /= self.scales[:, j : j + 1]
+            weight[:, sl] += self.zeros[:, j : j + 1]
+        weight = weight.clamp_(min=0, max=2**self.bits - 1).to(dtype=torch.uint8)
+        self.quant_weight.zero_()
+        for nr in range(self.entries_per_byte):
+            self.quant_weight += weight[:, nr :: self.entries_per_byte] << (nr * self.bits)
+        self._tiled = None
+
+    # ------------------------------------------------------------------ device paths
+    def _check_layout(self):
+        qw = self.quant_weight
+        if tuple(qw.stride()) != (1, self.out_features) and qw.numel() > 0 and self.out_features > 1 and qw.shape[1] > 1:
+            raise RuntimeError(
+                f"quant_weight strides {tuple(qw.stride())} differ from the reference layout (1, {self.out_features})")
+        if not self.scales.is_contiguous() or not self.zeros.is_contiguous():
+            raise RuntimeError("scales/zeros must be contiguous")
+
+    def get_weight(self, dtype=torch.float):
+        """quantization.py:392-411, on the GPU, bit-exact with the reference arithmetic."""
+        L.require_cuda_bf16(torch.empty(0, device=self.quant_weight.device, dtype=torch.bfloat16), "get_weight")
+        self._check_layout()
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise RuntimeError(f"get_weight dtype {dtype} unsupported (bf16 or fp32)")
+        out = torch.empty((self.out_features, self.in_features), device=self.quant_weight.device, dtype=dtype)
+        rc = L.lib().b2l_q_dequant(self.quant_weight.data_ptr(), self.scales.data_ptr(), self.zeros.data_ptr(),
+                                   L.sz_dtype_of(self.scales), out.data_ptr(),
+                                   L.B2L_BF16 if dtype == torch.bfloat16 else L.B2L_F32, self.out_features,
+                                   self.in_features, self.bits, self.tile_cols, L.stream_ptr())
+        L.check(rc, "b2l_q_dequant")
+        return out
+
+    @property
+    def tc_capable(self) -> bool:
+        """Eligible for the tcgen05 kernel: 4 bits, one (scale, zero) per row, K % 32 == 0, no bias."""
+        return (self.bits == 4 and self.scales.shape[1] == 1 and self.in_features % 32 == 0 and self.bias is None
+                and self.zeros.dtype == self.scales.dtype)
+
+    def tiled(self) -> torch.Tensor:
+        """The [N/128][K/32][128][16 B] re-tiling (b2l_q4_tile), rebuilt when quant_weight changes."""
+        qw = self.quant_weight
+        key = (qw.data_ptr(), qw._version)
+        if self._tiled is None or self._tiled_key != key:
+            self._check_layout()
+            nbytes = L.lib().b2l_q4_tiled_bytes(self.out_features, self.in_features)
+            t = torch.empty(nbytes, dtype=torch.uint8, device=qw.device)
+            L.check(L.lib().b2l_q4_tile(qw.data_ptr(), t.data_ptr(), self.out_features, self.in_features, L.stream_ptr()),
+                    "b2l_q4_tile")
+            self._tiled, self._tiled_key = t, key
+        return self._tiled
+
+    def forward(self, inp):
+        L.require_cuda_bf16(inp, "ColBlockQuantizedLinear.forward")
+        if self.quant_weight.device != inp.device:
+            raise RuntimeError("input and quant_weight are on different devices")
+        shape = inp.shape
+        x = inp.reshape(-1, shape[-1])
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        M, K, N = x.shape[0], self.in_features, self.out_features
+        assert shape[-1] == K, "incompatible dimensions"
+        y = torch.empty((M, N), device=inp.device, dtype=inp.dtype)
+        if M == 0:
+            return y.reshape(*shape[:-1], N)
+        aligned = x.data_ptr() % 16 == 0 and x.stride(0) % 8 == 0
+        if self.tc_capable and aligned and M <= 64:
+            qt = self.tiled()
+            for m0 in range(0, M, 16):
+                mm = min(16, M - m0)
+                a = L.Q4LinearArgs(
+                    x=x[m0:].data_ptr(), ldx=x.stride(0), qw_tiled=qt.data_ptr(), scales=self.scales.data_ptr(),
+                    zeros=self.zeros.data_ptr(), sz_dtype=L.sz_dtype_of(self.scales), y=y[m0:].data_ptr(), ldy=N,
+                    M=mm, N=N, K=K, prologue=L.PRO_NONE, norm_scale=None, eps=0.0, epilogue=L.EPI_STORE, res=None,
+                    ldres=0, split_k=0, flags=0)
+                L.check(L.lib().b2l_q4_linear_tc(C.byref(a), L.stream_ptr()), "b2l_q4_linear_tc")
+        elif M > 64 and self.bias is None:
+            # prefill-shaped: materialise the dense weight with the reference's own rounding
+            # (get_weight) and run the plain library GEMM, as quantization.py:422-423 does
+            y = torch.nn.functional.linear(x, self.get_weight(inp.dtype))
+        else:
+            self._check_layout()
+            rc = L.lib().b2l_q_linear(x.data_ptr(), x.stride(0), self.quant_weight.data_ptr(), self.scales.data_ptr(),
+                                      self.zeros.data_ptr(), L.sz_dtype_of(self.scales),
+                                      None if self.bias is None else self.bias.to(inp.dtype).data_ptr(), y.data_ptr(), N,
+                                      M, N, K, self.bits, self.tile_cols, L.stream_ptr())
+            L.check(rc, "b2l_q_linear")
+        return y.reshape(*shape[:-1], N)
+
+
+def qlinear_4bit_weight(inp, weight, scales, zeros):
+    """Same call as the reference's Triton launcher (quantization.py:284-333):
+    `weight` is quant_weight (N, K/2) in the reference layout, scales/zeros (N, 1)."""
+    L.require_cuda_bf16(inp, "qlinear_4bit_weight")
+    N, K = weight.shape[0], weight.shape[1] * 2
+    assert inp.shape[-1] == K, "incompatible dimensions"
+    assert scales.shape == (N, 1) and zeros.shape == (N, 1)
+    x = inp.reshape(-1, K).contiguous()
+    y = torch.empty((x.shape[0], N), device=inp.device, dtype=inp.dtype)
+    if tuple(weight.stride()) != (1, N):
+        weight = weight.t().contiguous().t()
+    scales, zeros = scales.contiguous(), zeros.contiguous()
+    rc = L.lib().b2l_q_linear(x.data_ptr(), K, weight.data_ptr(), scales.data_ptr(), zeros.data_ptr(), L.sz_dtype_of(scales),
+                              None, y.data_ptr(), N, x.shape[0], N, K, 4, K, L.stream_ptr())
+    L.check(rc, "b2l_q_linear")
+    return y.reshape(*inp.shape[:-1], N)

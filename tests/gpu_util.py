@@ -1,0 +1,28 @@
+"""Helpers shared by the -m gpu parity tests."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from diag import rand_q4, ref_linear, relerr, tc_call, tile  # noqa: E402,F401
+
+
+def build_tiny(dev, cfg, mode="gptq.int4", seed=1234, tile_cols=-1):
+    import lit_llama_b200 as P
+    from lit_llama_b200.utils import quantization
+    from oracle import llama_oracle as O
+
+    sd = O.synth_state_dict(cfg["n_layer"], cfg["n_head"], cfg["n_embd"], cfg["vocab_size"], mode, dtype=torch.bfloat16, seed=seed)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(dev), quantization(mode):
+            model = P.LLaMA(P.LLaMAConfig(**cfg))
+    finally:
+        torch.set_default_dtype(prev)
+    model.load_state_dict(sd)
+    oracle = O.OracleLLaMA.from_state_dict(sd, cfg["n_layer"], cfg["n_head"], cfg["block_size"], mode)
+    return model.eval(), oracle, sd

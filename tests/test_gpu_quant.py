@@ -1,0 +1,155 @@
+"""-m gpu: the quantized linears through the C ABI against the oracle / golden vectors.
+
+Bars: integer work (unpack, dequant in a given dtype, re-tiling) bit-exact; linear outputs
+normwise within 1e-3 of exact arithmetic (north_star) and within the reference's own bf16
+tolerance (tests/test_model.py:133) of the reference's CPU forward."""
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+from oracle import llama_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+def _module(case, dev, dtype):
+    from lit_llama_b200.quantization import ColBlockQuantizedLinear
+
+    out_f, in_f = case["w"].shape
+    lin = ColBlockQuantizedLinear(in_f, out_f, False, bits=case["bits"], tile_cols=case["groupsize"]).to(dev)
+    lin.load_state_dict({"quant_weight": case["quant_weight"], "scales": case["scales"].to(dtype), "zeros": case["zeros"].to(dtype)})
+    lin.scales = lin.scales.to(dtype)
+    lin.zeros = lin.zeros.to(dtype)
+    return lin
+
+
+def test_dequant_bit_exact_vs_reference(dev):
+    for c in load_golden("quant_cases.pt"):
+        lin = _module(c, dev, torch.float32)
+        assert tuple(lin.quant_weight.stride()) == c["qw_stride"]
+        assert torch.equal(lin.get_weight(torch.float32).cpu(), c["deq_f32"])
+        assert torch.equal(lin.get_weight(torch.bfloat16).cpu(), c["deq_bf16"])
+
+
+def test_linear_vs_reference_forward(dev):
+    for c in load_golden("quant_cases.pt"):
+        lin = _module(c, dev, torch.bfloat16)
+        x = c["x"].bfloat16().to(dev)
+        y = lin(x).float().cpu()
+        # reference's CPU bf16 forward (dense path), its own tolerance
+        torch.testing.assert_close(y, c["y_bf16"].float(), rtol=1e-3, atol=5e-3)
+        # exact arithmetic on the same stored parameters
+        tc = c["w"].shape[1] if c["groupsize"] == -1 else c["groupsize"]
+        exact = O.qlinear_exact(x.cpu().float(), c["quant_weight"], c["scales"].bfloat16(), c["zeros"].bfloat16(), c["bits"], tc)
+        assert (y - exact).norm() / exact.norm() < 1e-3 + 2.0 ** -9
+
+
+def test_tile_roundtrip_bit_exact(dev):
+    from gpu_util import rand_q4, tile
+    from lit_llama_b200 import _lib as L
+
+    for N, K in [(128, 64), (130, 256), (96, 128), (4096, 4096), (11008, 4096)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=N)
+        qt = tile(L, qw, N, K)
+        back = torch.empty_like(qw)
+        L.check(L.lib().b2l_q4_untile(qt.data_ptr(), back.data_ptr(), N, K, L.stream_ptr()), "untile")
+        assert torch.equal(back, qw)
+        # documented layout, decoded independently on the host for a few words
+        w = qt.view(torch.int32).reshape(-1, K // 32, 128, 4).cpu()
+        lvc = lv.cpu()
+        for (nt, ks, r, i) in [(0, 0, 0, 0), (0, K // 32 - 1, 5, 3), ((N - 1) // 128, 1 % (K // 32), (N - 1) % 128, 2)]:
+            word = int(w[nt, ks, r, i]) & 0xFFFFFFFF
+            for s in range(8):
+                k = ks * 32 + 8 * i + (2 * s if s < 4 else 2 * (s - 4) + 1)
+                assert ((word >> (4 * s)) & 0xF) == int(lvc[nt * 128 + r, k])
+
+
+@pytest.mark.parametrize("N,K,M,S", [(128, 64, 1, 1), (128, 96, 1, 1), (128, 256, 3, 1), (128, 256, 1, 2), (256, 512, 1, 4),
+                                     (256, 1024, 8, 8), (130, 256, 2, 2), (128, 1024, 16, 2), (384, 4096, 1, 0)])
+def test_tc_linear_small(dev, N, K, M, S):
+    from gpu_util import rand_q4, ref_linear, relerr, tc_call, tile
+    from lit_llama_b200 import _lib as L
+
+    lv, qw, sc, z = rand_q4(N, K, dev, seed=N + K + M)
+    qt = tile(L, qw, N, K)
+    x = torch.randn(M, K, device=dev).bfloat16()
+    y, err = tc_call(L, x, qt, sc, z, N, K, split_k=S)
+    torch.cuda.synchronize()
+    assert err is None, err
+    want = ref_linear(x, lv, sc, z)
+    assert relerr(y, want) < 1e-3 + 2.0 ** -9  # bf16 output rounding alone is up to 2^-9 normwise
+    # against the exact result rounded to bf16: at most 1 ulp apart, almost everywhere equal
+    wb = want.float().bfloat16()
+    assert float((y == wb).float().mean()) > 0.98
+
+
+@pytest.mark.parametrize("name,N,K", [("c_attn", 12288, 4096), ("c_proj", 4096, 4096), ("c_fc12", 22016, 4096),
+                                      ("mlp_proj", 4096, 11008), ("lm_head", 32000, 4096)])
+def test_tc_linear_7b_shapes(dev, name, N, K):
+    """Full BASELINE sizes: agreement with fp64 math, with the independent generic kernel,
+    and linearity y(a+b) = y(a) + y(b) (size-independent property)."""
+    from gpu_util import rand_q4, ref_linear, relerr, tc_call, tile
+    from lit_llama_b200 import _lib as L
+
+    lv, qw, sc, z = rand_q4(N, K, dev, seed=7)
+    qt = tile(L, qw, N, K)
+    x = torch.randn(2, K, device=dev).bfloat16()
+    y, err = tc_call(L, x, qt, sc, z, N, K)
+    assert err is None, err
+    want = ref_linear(x, lv, sc, z)
+    assert relerr(y, want) < 1e-3 + 2.0 ** -9
+    yg = torch.empty(2, N, device=dev, dtype=torch.bfloat16)
+    rc = L.lib().b2l_q_linear(x.data_ptr(), K, qw.data_ptr(), sc.data_ptr(), z.data_ptr(), L.sz_dtype_of(sc), None, yg.data_ptr(), N, 2, N, K, 4, K, L.stream_ptr())
+    assert rc == 0
+    assert relerr(y, yg) < 3e-3
+    xs = (x[0:1].float() + x[1:2].float()).bfloat16()
+    ys, err = tc_call(L, xs, qt, sc, z, N, K)
+    assert err is None
+    lin = ref_linear(xs, lv, sc, z)
+    assert relerr(ys, lin) < 1e-3 + 2.0 ** -9
+
+
+def test_tc_prologue_epilogue(dev):
+    from gpu_util import rand_q4, ref_linear, relerr, tc_call, tile
+    from lit_llama_b200 import _lib as L
+
+    N, K, M = 512, 1024, 2
+    lv, qw, sc, z = rand_q4(N, K, dev, seed=5)
+    qt = tile(L, qw, N, K)
+    x = (torch.randn(M, K, device=dev) * 0.7).bfloat16()
+    g = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
+    xn = O.rmsnorm(x.cpu(), g.cpu()).to(dev)  # oracle RMSNorm (bf16 rounding points)
+    y, err = tc_call(L, x, qt, sc, z, N, K, prologue=1, norm_scale=g, eps=1e-5)
+    assert err is None, err
+    assert relerr(y, ref_linear(xn, lv, sc, z)) < 1e-3 + 2.0 ** -9
+    res = torch.randn(M, N, device=dev).bfloat16()
+    y, err = tc_call(L, x, qt, sc, z, N, K, epilogue=1, res=res)
+    assert err is None, err
+    want = ref_linear(x, lv, sc, z).float().bfloat16() + res
+    assert float((y == want).float().mean()) > 0.98 and relerr(y, want) < 2e-3
+    buf = res.clone()
+    _, err = tc_call(L, x, qt, sc, z, N, K, epilogue=1, res=buf, y=buf)
+    assert err is None and torch.equal(buf, y)
+    full = ref_linear(x, lv, sc, z).float().bfloat16().reshape(M, N // 128, 2, 64)
+    a, b = full[:, :, 0].reshape(M, -1), full[:, :, 1].reshape(M, -1)
+    want = torch.nn.functional.silu(a) * b
+    y, err = tc_call(L, x, qt, sc, z, N, K, epilogue=2, n_out=N // 2)
+    assert err is None, err
+    assert relerr(y, want) < 4e-3 and float((y == want).float().mean()) > 0.9
+
+
+def test_unsupported_shapes_raise(dev):
+    from lit_llama_b200.quantization import ColBlockQuantizedLinear
+
+    lin = ColBlockQuantizedLinear(64, 16, False, bits=4, tile_cols=-1).to(dev)
+    with pytest.raises(RuntimeError):
+        lin(torch.zeros(1, 64, device=dev))  # fp32 activations: no silent fallback
+    with pytest.raises(RuntimeError):
+        lin(torch.zeros(1, 64, dtype=torch.bfloat16))  # CPU tensor

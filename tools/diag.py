@@ -1,0 +1,433 @@
+"""GPU diagnostics: exercises every kernel against torch math and PRINTS errors instead
+of asserting, section by section, each in its own subprocess with a timeout (a hung
+kernel only loses its section).  Usage on the GPU box:
+
+    python tools/diag.py            # all sections
+    python tools/diag.py tc_small   # one section
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "ops", "model", "bench_layers", "bench_step"]
+
+
+def rand_q4(N, K, dev, seed=0, sz_dtype=None, groups=1, bits=4):
+    import torch
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sz_dtype = sz_dtype or torch.bfloat16
+    maxq = 2**bits - 1
+    lv = torch.randint(0, maxq + 1, (N, K), generator=g, dtype=torch.uint8)
+    epb = 8 // bits
+    qw = torch.zeros((N, K // epb), dtype=torch.uint8)
+    for nr in range(epb):
+        qw |= lv[:, nr::epb] << (nr * bits)
+    qw = qw.t().contiguous().t()
+    scales = (torch.rand(N, groups, generator=g) * 0.01 + 0.002).to(sz_dtype)
+    zeros = torch.randint(0, maxq + 1, (N, groups), generator=g).to(sz_dtype)
+    return lv.to(dev), qw.to(dev), scales.to(dev), zeros.to(dev)
+
+
+def ref_linear(x, lv, scales, zeros, tile_cols=None):
+    import torch
+
+    N, K = lv.shape
+    tc = K if tile_cols is None else tile_cols
+    ng = scales.shape[1]
+    w = lv.double()
+    for g in range(ng):
+        sl = slice(g * tc, (g + 1) * tc)
+        w[:, sl] = (w[:, sl] - zeros[:, g : g + 1].double()) * scales[:, g : g + 1].double()
+    return (x.double() @ w.t())
+
+
+def relerr(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def tc_call(L, x, qt, scales, zeros, N, K, *, y=None, prologue=0, norm_scale=None, eps=1e-5, epilogue=0, res=None,
+            split_k=0, flags=0, n_out=None):
+    import torch
+
+    M = x.shape[0]
+    n_out = n_out or N
+    if y is None:
+        y = torch.zeros((M, n_out), device=x.device, dtype=torch.bfloat16)
+    a = L.Q4LinearArgs(x=x.data_ptr(), ldx=x.stride(0), qw_tiled=qt.data_ptr(), scales=scales.data_ptr(),
+                       zeros=zeros.data_ptr(), sz_dtype=L.sz_dtype_of(scales), y=y.data_ptr(), ldy=y.stride(0), M=M, N=N,
+                       K=K, prologue=prologue, norm_scale=None if norm_scale is None else norm_scale.data_ptr(),
+                       eps=eps, epilogue=epilogue, res=None if res is None else res.data_ptr(),
+                       ldres=0 if res is None else res.stride(0), split_k=split_k, flags=flags)
+    rc = L.lib().b2l_q4_linear_tc(C.byref(a), L.stream_ptr())
+    if rc != 0:
+        return None, f"rc={rc}: {L.lib().b2l_last_error().decode()}"
+    return y, None
+
+
+def tile(L, qw, N, K):
+    import torch
+
+    qt = torch.empty(L.lib().b2l_q4_tiled_bytes(N, K), dtype=torch.uint8, device=qw.device)
+    L.check(L.lib().b2l_q4_tile(qw.data_ptr(), qt.data_ptr(), N, K, L.stream_ptr()), "tile")
+    return qt
+
+
+def sec_generic():
+    import torch
+    from lit_llama_b200 import _lib as L
+    from lit_llama_b200.quantization import ColBlockQuantizedLinear
+
+    dev = torch.device("cuda")
+    for bits, groups, N, K, M in [(4, 1, 24, 64, 3), (4, 4, 24, 128, 1), (8, 1, 16, 64, 5), (8, 3, 8, 96, 2), (4, 1, 130, 256, 1),
+                                  (4, 1, 4096, 4096, 1), (4, 1, 12288, 4096, 2)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=bits + N, groups=groups, bits=bits)
+        tc = K // groups
+        lin = ColBlockQuantizedLinear(K, N, False, bits=bits, tile_cols=tc if groups > 1 else -1).to(dev)
+        lin.quant_weight.copy_(qw); lin.scales = sc; lin.zeros = z
+        x = torch.randn(M, K, device=dev).bfloat16()
+        y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        rc = L.lib().b2l_q_linear(x.data_ptr(), K, lin.quant_weight.data_ptr(), sc.data_ptr(), z.data_ptr(), L.sz_dtype_of(sc), None,
+                                  y.data_ptr(), N, M, N, K, bits, tc, L.stream_ptr())
+        torch.cuda.synchronize()
+        want = ref_linear(x, lv, sc, z, tc)
+        print(f"generic bits={bits} groups={groups} N={N} K={K} M={M}: rc={rc} relerr={relerr(y, want):.2e}")
+        for dt in (torch.float32, torch.bfloat16):
+            w = lin.get_weight(dt)
+            wr = lv.float().to(dt)
+            for g in range(groups):
+                sl = slice(g * tc, (g + 1) * tc)
+                wr[:, sl] -= z[:, g : g + 1]
+                wr[:, sl] *= sc[:, g : g + 1]
+            print(f"   dequant {dt}: bit-exact={bool(torch.equal(w, wr))}")
+
+
+def sec_tile():
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    for N, K in [(128, 64), (130, 256), (4096, 4096), (96, 128)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=N)
+        qt = tile(L, qw, N, K)
+        back = torch.empty_like(qw)
+        L.check(L.lib().b2l_q4_untile(qt.data_ptr(), back.data_ptr(), N, K, L.stream_ptr()), "untile")
+        torch.cuda.synchronize()
+        # independent check of the documented layout on the host
+        w = qt.view(torch.int32).reshape(-1, K // 32, 128, 4).cpu()
+        lvc = lv.cpu()
+        ok = True
+        for (nt, ks, r, i) in [(0, 0, 0, 0), (0, K // 32 - 1, 5, 3), ((N - 1) // 128, 1 % (K // 32), (N - 1) % 128, 2)]:
+            word = int(w[nt, ks, r, i]) & 0xFFFFFFFF
+            o = nt * 128 + r
+            for s in range(8):
+                k = ks * 32 + 8 * i + (2 * s if s < 4 else 2 * (s - 4) + 1)
+                ok &= ((word >> (4 * s)) & 0xF) == int(lvc[o, k])
+        print(f"tile N={N} K={K}: roundtrip={bool(torch.equal(back, qw))} layout_spot={ok}")
+
+
+def sec_tc_small():
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    N, K, M = 128, 64, 1
+    lv, qw, sc, z = rand_q4(N, K, dev, seed=1)
+    qt = tile(L, qw, N, K)
+    x = torch.randn(M, K, device=dev).bfloat16()
+    y, err = tc_call(L, x, qt, sc, z, N, K, split_k=1)
+    torch.cuda.synchronize()
+    print("tc_small first call:", err or "launched")
+    want = ref_linear(x, lv, sc, z)
+    print(f"  N=128 K=64 M=1 S=1 relerr={relerr(y, want):.3e}")
+    print("  got ", [round(float(v), 4) for v in y[0, :6]])
+    print("  want", [round(float(v), 4) for v in want[0, :6]])
+    # hypotheses if wrong: pair order swapped inside a TMEM column / B rows
+    xs = x.clone().reshape(M, K // 2, 2).flip(-1).reshape(M, K)
+    print(f"  hypothesis pair-swapped relerr={relerr(y, ref_linear(xs, lv, sc, z)):.3e}")
+    xh = x.clone().reshape(M, K // 16, 2, 8).flip(2).reshape(M, K)
+    print(f"  hypothesis k-halves-swapped relerr={relerr(y, ref_linear(xh, lv, sc, z)):.3e}")
+    for (N, K, M, S) in [(128, 64, 1, 1), (128, 128, 1, 1), (128, 256, 3, 1), (128, 256, 1, 2), (256, 512, 1, 4), (256, 1024, 8, 8),
+                         (128, 96, 1, 1), (384, 4096, 1, 4), (130, 256, 2, 2), (128, 1024, 16, 2), (128, 1024, 9, 2)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=N + K)
+        qt = tile(L, qw, N, K)
+        x = torch.randn(M, K, device=dev).bfloat16()
+        for flags in (0, 2):
+            if flags == 2 and M > 8:
+                continue
+            y, err = tc_call(L, x, qt, sc, z, N, K, split_k=S, flags=flags)
+            torch.cuda.synchronize()
+            if err:
+                print(f"  N={N} K={K} M={M} S={S} flags={flags}: {err}")
+                continue
+            want = ref_linear(x, lv, sc, z)
+            wb = want.float().bfloat16()
+            print(f"  N={N} K={K} M={M} S={S} flags={flags}: relerr={relerr(y, want):.3e} exact_bf16_frac={float((y == wb).float().mean()):.4f}")
+
+
+def sec_tc_shapes():
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    for (N, K) in [(12288, 4096), (4096, 4096), (22016, 4096), (4096, 11008), (32000, 4096)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=N % 1000 + K)
+        qt = tile(L, qw, N, K)
+        for M in (1, 8):
+            x = torch.randn(M, K, device=dev).bfloat16()
+            for S in (0, 1, 2, 4, 8):
+                y, err = tc_call(L, x, qt, sc, z, N, K, split_k=S)
+                torch.cuda.synchronize()
+                if err:
+                    print(f"  N={N} K={K} M={M} S={S}: {err}")
+                    continue
+                want = ref_linear(x, lv, sc, z)
+                print(f"  N={N} K={K} M={M} S={S}: relerr={relerr(y, want):.3e}")
+        del lv, qw, qt
+
+
+def sec_tc_modes():
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    N, K, M = 512, 1024, 2
+    lv, qw, sc, z = rand_q4(N, K, dev, seed=5)
+    qt = tile(L, qw, N, K)
+    x = (torch.randn(M, K, device=dev) * 0.7).bfloat16()
+    g = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
+    # rmsnorm prologue (bf16 rounding points of model.py:270-277 via torch bf16 ops)
+    ms = torch.mean(x * x, dim=-1, keepdim=True)
+    xn = g * (x * torch.rsqrt(ms + 1e-5))
+    y, err = tc_call(L, x, qt, sc, z, N, K, prologue=1, norm_scale=g, eps=1e-5)
+    torch.cuda.synchronize()
+    print("rmsnorm prologue:", err or f"relerr={relerr(y, ref_linear(xn, lv, sc, z)):.3e}")
+    # residual epilogue
+    res = torch.randn(M, N, device=dev).bfloat16()
+    y, err = tc_call(L, x, qt, sc, z, N, K, epilogue=1, res=res)
+    torch.cuda.synchronize()
+    want = (ref_linear(x, lv, sc, z).float().bfloat16() + res)
+    print("residual epilogue:", err or f"relerr={relerr(y, want):.3e} exact={float((y == want).float().mean()):.4f}")
+    # in-place residual
+    buf = res.clone()
+    y, err = tc_call(L, x, qt, sc, z, N, K, epilogue=1, res=buf, y=buf)
+    torch.cuda.synchronize()
+    print("in-place residual:", err or f"relerr={relerr(buf, want):.3e}")
+    # swiglu: rows interleaved [64 a | 64 b]
+    full = ref_linear(x, lv, sc, z).float().bfloat16().reshape(M, N // 128, 2, 64)
+    a, b = full[:, :, 0].reshape(M, -1), full[:, :, 1].reshape(M, -1)
+    want = torch.nn.functional.silu(a) * b
+    y, err = tc_call(L, x, qt, sc, z, N, K, epilogue=2, n_out=N // 2)
+    torch.cuda.synchronize()
+    print("swiglu epilogue:", err or f"relerr={relerr(y, want):.3e} exact={float((y == want).float().mean()):.4f}")
+    # pdl flag outside a chain
+    y, err = tc_call(L, x, qt, sc, z, N, K, flags=1)
+    torch.cuda.synchronize()
+    print("pdl flag:", err or f"relerr={relerr(y, ref_linear(x, lv, sc, z)):.3e}")
+    # fp32 scales/zeros
+    lv, qw, sc, z = rand_q4(N, K, dev, seed=6, sz_dtype=torch.float32)
+    qt = tile(L, qw, N, K)
+    y, err = tc_call(L, x, qt, sc, z, N, K)
+    torch.cuda.synchronize()
+    print("fp32 scales:", err or f"relerr={relerr(y, ref_linear(x, lv, sc, z)):.3e}")
+
+
+def sec_ops():
+    import torch
+    import lit_llama_b200 as P
+    from lit_llama_b200.utils import quantization
+    from oracle import llama_oracle as O
+
+    dev = torch.device("cuda")
+    x = torch.randn(3, 5, 4096, device=dev).bfloat16()
+    n = P.RMSNorm(4096).to(dev).bfloat16()
+    n.scale.data = (1 + 0.1 * torch.randn(4096, device=dev)).bfloat16()
+    y = n(x)
+    want = O.rmsnorm(x.cpu(), n.scale.data.cpu())
+    print(f"rmsnorm: exact_frac={float((y.cpu() == want).float().mean()):.5f} relerr={relerr(y.cpu(), want):.2e}")
+    tab = O.rope_table(64, 128).to(dev)
+    xr = torch.randn(2, 9, 4, 128, device=dev).bfloat16()
+    yr = P.apply_rope(xr, tab)
+    wr = O.rope_apply(xr.cpu(), tab.cpu())
+    print(f"rope: exact_frac={float((yr.cpu() == wr).float().mean()):.5f}")
+
+
+def _tiny(dev, cfg, mode="gptq.int4", seed=1234):
+    import torch
+    import lit_llama_b200 as P
+    from lit_llama_b200.utils import quantization
+    from oracle import llama_oracle as O
+
+    sd = O.synth_state_dict(cfg["n_layer"], cfg["n_head"], cfg["n_embd"], cfg["vocab_size"], mode, dtype=torch.bfloat16, seed=seed)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(dev), quantization(mode):
+            model = P.LLaMA(P.LLaMAConfig(**cfg))
+    finally:
+        torch.set_default_dtype(prev)
+    model.load_state_dict(sd)
+    return model.eval(), O.OracleLLaMA.from_state_dict(sd, cfg["n_layer"], cfg["n_head"], cfg["block_size"], mode)
+
+
+def sec_model():
+    import torch
+    import lit_llama_b200 as P
+    from lit_llama_b200.utils import quantization
+    from oracle import llama_oracle as O
+
+    dev = torch.device("cuda")
+    cfg = dict(block_size=64, vocab_size=96, n_layer=2, n_head=4, n_embd=128)
+    gd = torch.load(os.path.join(ROOT, "tests/golden/tiny_int4_bf16.pt"), weights_only=False)
+    for graph_after in (0, 2):
+        model, orc = _tiny(dev, cfg)
+        model.graph_after = graph_after
+        prompt = gd["prompt"]
+        S = 16
+        with torch.no_grad():
+            got = [model(prompt.view(1, -1).to(dev), S, torch.arange(7, device=dev))]
+            for i, t in enumerate(gd["steps_tokens"] + [4, 9, 60]):
+                got.append(model(torch.tensor([[t]], device=dev), S, torch.tensor([7 + i], device=dev)))
+        torch.cuda.synchronize()
+        for i, (g_, w_) in enumerate(zip(got, gd["steps_logits"])):
+            d = (g_.float().cpu() - w_.float())
+            print(f"model graph_after={graph_after} step {i}: max_abs={float(d.abs().max()):.4f} relerr={relerr(g_.cpu(), w_):.3e}")
+        k0 = model.kv_caches[0][0].float().cpu()
+        print(f"   kv0_k relerr={relerr(k0[:, :, :10], gd['kv0_k'][:, :, :10]):.3e}")
+    # generate: greedy tokens vs golden, roll branch
+    model, orc = _tiny(dev, cfg)
+    with torch.no_grad():
+        y = P.generate(model, gd["prompt"].to(torch.int32).to(dev), 12, top_k=1)
+    print("generate greedy match:", bool(torch.equal(y.cpu(), gd["gen_greedy"])), y.cpu().tolist(), gd["gen_greedy"].tolist())
+    model.reset_cache()
+    torch.manual_seed(99)
+    with torch.no_grad():
+        y = P.generate(model, gd["prompt"].to(torch.int32).to(dev), 12, max_seq_length=10, top_k=4)
+    print("generate roll len:", y.shape, y.cpu().tolist(), "golden(cpu rng)", gd["gen_roll"].tolist())
+    # roll-branch logits vs golden
+    model.reset_cache()
+    S2 = 8
+    with torch.no_grad():
+        got = [model(gd["prompt"].view(1, -1).to(dev), S2, torch.arange(7, device=dev))[:, -1]]
+        for i, t in enumerate(gd["roll_tokens"]):
+            got.append(model(torch.tensor([[t]], device=dev), S2, torch.tensor([7 + i], device=dev))[:, -1])
+    for i, (g_, w_) in enumerate(zip(got, gd["roll_logits"])):
+        print(f"roll step {i}: max_abs={float((g_.float().cpu() - w_.float()).abs().max()):.4f} relerr={relerr(g_.cpu(), w_):.3e}")
+    kl = model.logical_kv_caches()[1][0]
+    print(f"   roll kv1_k relerr={relerr(kl.cpu(), gd['roll_kv1_k']):.3e}")
+    # no-cache forward
+    model.reset_cache()
+    with torch.no_grad():
+        lg = model(gd["prompt"].view(1, -1).to(dev))
+    print(f"nocache relerr={relerr(lg.cpu(), gd['nocache_logits']):.3e}")
+
+
+def _time(fn, iters=20, warm=3):
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3  # us
+
+
+def sec_bench_layers():
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for (name, N, K) in [("c_attn", 12288, 4096), ("c_proj", 4096, 4096), ("fc12", 22016, 4096), ("mlp_proj", 4096, 11008), ("lm_head", 32000, 4096)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=3)
+        # several copies so that successive calls do not hit L2
+        n_copies = max(2, int(300e6 // (N * K // 2)) + 1)
+        qts = [tile(L, qw, N, K) for _ in range(n_copies)]
+        x = torch.randn(1, K, device=dev).bfloat16()
+        y = torch.zeros(1, N, device=dev, dtype=torch.bfloat16)
+        for S in (1, 2, 4, 8):
+            for flags in (0, 2):
+                it = [0]
+
+                def fn():
+                    tc_call(L, x, qts[it[0] % n_copies], sc, z, N, K, y=y, split_k=S, flags=flags)
+                    it[0] += 1
+
+                us = _time(fn, iters=40)
+                gbs = (N * K / 2) / us / 1e3
+                print(f"{name} N={N} K={K} S={S} flags={flags}: {us:.2f} us  {gbs:.0f} GB/s")
+        # generic kernel for comparison
+        yb = torch.zeros(1, N, device=dev, dtype=torch.bfloat16)
+
+        def fg():
+            L.lib().b2l_q_linear(x.data_ptr(), K, qw.data_ptr(), sc.data_ptr(), z.data_ptr(), 0, None, yb.data_ptr(), N, 1, N, K, 4, K, L.stream_ptr())
+
+        us = _time(fg, iters=10)
+        print(f"{name} generic: {us:.2f} us  {(N * K / 2) / us / 1e3:.0f} GB/s")
+        del qts
+
+
+def sec_bench_step():
+    import torch
+    import lit_llama_b200 as P
+    from lit_llama_b200.utils import quantization
+    from bench import build_synthetic_model
+
+    dev = torch.device("cuda")
+    model = build_synthetic_model("7B", dev)
+    S = 2048
+    for pdl in (1, 0):
+        for graph_after in (2, 0):
+            model.reset_cache()
+            model.decode_flags = pdl
+            model.graph_after = graph_after
+            model.copy_logits = False
+            idx = torch.randint(0, 32000, (1, 16), device=dev, dtype=torch.int32)
+            with torch.no_grad():
+                model(idx, S, torch.arange(16, device=dev))
+                tok = torch.randint(0, 32000, (1, 1), device=dev, dtype=torch.int32)
+                pos = [torch.tensor([16 + i], device=dev) for i in range(64)]
+                for i in range(4):
+                    model(tok, S, pos[i])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(4, 64):
+                    model(tok, S, pos[i])
+                e1.record()
+                torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 60 * 1e3
+            print(f"decode step 7B pos~16-80 pdl={pdl} graph={graph_after > 0}: {us:.1f} us/token  {1e6 / us:.1f} tok/s")
+
+
+def main():
+    which = sys.argv[1:] or SECTIONS
+    if len(which) == 1 and os.environ.get("B2L_DIAG_CHILD") == "1":
+        globals()["sec_" + which[0]]()
+        return
+    for s in which:
+        print(f"===== {s} =====", flush=True)
+        t0 = time.time()
+        env = dict(os.environ, B2L_DIAG_CHILD="1")
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), s], env=env, timeout=420, capture_output=True, text=True)
+            print(r.stdout[-6000:])
+            if r.returncode != 0:
+                print(f"[{s}] exit code {r.returncode}\n{r.stderr[-3000:]}")
+        except subprocess.TimeoutExpired as e:
+            print(f"[{s}] TIMEOUT after 420 s\n{(e.stdout or b'')[-3000:]}")
+        print(f"[{s}] {time.time() - t0:.1f} s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
