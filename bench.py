@@ -244,6 +244,23 @@ def time_q4_launches(model, dev):
     return e0.elapsed_time(e1) / reps * 1e-3, len(calls)  # seconds per token's worth of launches
 
 
+def reduce_max(times, device):
+    """Max over ranks of per-rank times (the N > 1 rule of the bench contract).  Replicas
+    share nothing else: there is no data-path collective."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor(times, device=device, dtype=torch.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def aggregate_throughput(world, steps, t_max):
+    """Whole-job tokens/s of `world` replicas that each decoded `steps` tokens."""
+    return world * steps / t_max
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,10 +345,7 @@ def main():
 
         t_q4, n_q4 = time_q4_launches(model, dev)
 
-    times = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e = float(times[0]), float(times[1])
+    t_dev, t_e2e = reduce_max([t_dev, t_e2e], dev)
 
     if rank == 0:
         W, kv = model_bytes(MODEL)
@@ -349,7 +363,7 @@ def main():
         import ctypes as C
         launches = L.lib().b2l_decode_step_launches(C.byref(model._decode.args))
         line = {
-            "metric": "LLaMA-7B gptq.int4 decode tokens/sec", "value": world * K / t_dev, "unit": "tokens/s", "n_gpus": world,
+            "metric": "LLaMA-7B gptq.int4 decode tokens/sec", "value": aggregate_throughput(world, K, t_dev), "unit": "tokens/s", "n_gpus": world,
             "steps": K, "warmup": warm, "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "LLaMA-7B gptq.int4 decode batch=1 ctx=2048 (random-init weights)", "prompt_tokens": PROMPT_T,
@@ -357,7 +371,7 @@ def main():
                        "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                        "l2": "weights 3.31 GB per token >> 126 MB L2 (inputs larger than L2)"},
             "clocks": clk,
-            "e2e": {"value": world * Ke / t_e2e, "unit": "tokens/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 8, "steps": Ke},
+            "e2e": {"value": aggregate_throughput(world, Ke, t_e2e), "unit": "tokens/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 8, "steps": Ke},
             "gpu_launches": launches * K,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "kernel": "q4_linear_tc_kernel", "launches_per_token": n_q4, "bytes_per_token_launches": W,

@@ -102,6 +102,8 @@ typedef struct b2l_q4_linear_args {
   int ldres;
   int split_k;          /* cluster size along K: 1,2,4,8 (0 = library picks)          */
   int flags;            /* B2L_F_*                                                    */
+  void* trace;          /* debug: device uint64[256] receiving clock64() stamps of CTA 0
+                           (NULL = off); see tools/diag.py `trace`                     */
 } b2l_q4_linear_args;
 
 enum {

@@ -25,7 +25,7 @@ class Q4LinearArgs(C.Structure):
         ("M", c_int), ("N", c_int), ("K", c_int),
         ("prologue", c_int), ("norm_scale", c_void_p), ("eps", c_float),
         ("epilogue", c_int), ("res", c_void_p), ("ldres", c_int),
-        ("split_k", c_int), ("flags", c_int),
+        ("split_k", c_int), ("flags", c_int), ("trace", c_void_p),
     ]
 
 

@@ -164,6 +164,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32)
 // grid (B*n_head, T): merge the split partials and write y[b][t][h*hs + d] in bf16.
 __global__ void attn_combine_kernel(const float* __restrict__ work, __nv_bfloat16* __restrict__ y, int T,
                                     int n_head, int hs, int n_split) {
+  // the kernel after this one (attn.c_proj) may start streaming its weights now
+  pdl_launch_dependents();
   const int bh = blockIdx.x, b = bh / n_head, h = bh % n_head, t = blockIdx.y;
   const float* base = work + ((size_t)bh * T + t) * n_split * (hs + 2);
   float M = -INFINITY;

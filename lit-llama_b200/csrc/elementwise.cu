@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __res
 template <typename IdxT>
 __global__ void embedding_kernel(const IdxT* __restrict__ idx, const __nv_bfloat16* __restrict__ wte,
                                  __nv_bfloat16* __restrict__ out, int C, int vocab) {
+  pdl_launch_dependents();  // the first c_attn of the step may start streaming its weights
   long long t = (long long)idx[blockIdx.x];
   if (t < 0 || t >= vocab) t = 0;  // torch would raise; keep the kernel memory-safe
   const __nv_bfloat16* src = wte + (size_t)t * C;

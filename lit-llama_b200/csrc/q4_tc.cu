@@ -53,6 +53,7 @@ struct Params {
   int nst_ring;   // ring stages
   int kcb;        // bytes per 8-k core-matrix column of the B operand (256, or 128 when rows 8..15 alias)
   int kseg_max;   // max K elements of one rank
+  unsigned long long* trace;  // debug: clock64 stamps of CTA 0 (nullptr = off)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -168,6 +169,11 @@ __device__ __forceinline__ void unpack_word(uint32_t w, uint32_t* out) {
   out[3] = ((w >> 12) & 0x000f000fu) | 0x43004300u;
 }
 
+#define B2L_TRACE(slot)                                                      \
+  do {                                                                       \
+    if (p.trace != nullptr && blockIdx.x == 0) p.trace[(slot)] = clock64(); \
+  } while (0)
+
 // ---------------------------------------------------------------- shared memory map
 struct SmemLayout {
   uint32_t ring, xb, part, xsum, red, bars, tmem_slot, total;
@@ -212,6 +218,7 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
   const uint32_t bar_x_ready = bar_d_full + 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + L.tmem_slot);
 
+  if (tid == 0) B2L_TRACE(0);
   if (tid == 0) {
     for (int i = 0; i < p.nst_ring; ++i) {
       mbar_init(bar_w_full + i * 8, 1);
@@ -230,6 +237,7 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) B2L_TRACE(1);
 
   if (warp == 4) {
     // ===================== TMA producer: stream the packed slabs of this rank =====================
@@ -242,6 +250,7 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
         const uint32_t bytes = (uint32_t)ns * SLAB_BYTES;
         mbar_expect_tx(bar_w_full + slot * 8, bytes);
         tma_bulk_g2s(sbase + L.ring + slot * STAGE_BYTES, src + (size_t)st * STAGE_BYTES, bytes, bar_w_full + slot * 8);
+        if (st < 20) B2L_TRACE(108 + st);
       }
       // every weight byte of this CTA is now requested: let the next kernel's CTAs start
       pdl_launch_dependents();
@@ -258,6 +267,7 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
         const int ab = st % NAB, it = st / NAB;
         mbar_wait(bar_a_full + ab * 8, it & 1);
         tc_fence_after();
+        if (st < 20) B2L_TRACE(64 + st);
         const int ns = min(G, nslab - st * G);
         for (int s = 0; s < ns; ++s) {
 #pragma unroll
@@ -270,6 +280,7 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
           }
         }
         tc_commit(bar_a_empty + ab * 8);  // arrives when the MMAs above have read A
+        if (st < 20) B2L_TRACE(84 + st);
       }
       tc_commit(bar_d_full);
     }
@@ -278,6 +289,7 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
     // ===================== convert warps (thread = output row of the tile) =====================
     // -- activations: wait for the producing kernel, normalise, lay out as the B operand
     pdl_wait();
+    if (tid == 0) B2L_TRACE(2);
     float* xsum = reinterpret_cast<float*>(smem + L.xsum);
     float* red = reinterpret_cast<float*>(smem + L.red);
     {
@@ -344,6 +356,7 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
       fence_proxy_async_smem();  // B operand written with generic stores, read by the tensor core
       named_bar_sync(1, NCONV);
       if (tid == 0) mbar_arrive(bar_x_ready);
+      if (tid == 0) B2L_TRACE(3);
     }
 
     // -- weights: smem slab -> registers -> TMEM A operand
@@ -353,12 +366,14 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
       const int ab = st % NAB, ait = st / NAB;
       const int ns = min(G, nslab - st * G);
       mbar_wait(bar_w_full + slot * 8, rit & 1);
+      if (tid == 0 && st < 20) B2L_TRACE(4 + st);
       uint4 wv[G];
 #pragma unroll
       for (int s = 0; s < G; ++s)
         if (s < ns) wv[s] = *reinterpret_cast<const uint4*>(smem + L.ring + slot * STAGE_BYTES + s * SLAB_BYTES + tid * 16);
       mbar_wait(bar_a_empty + ab * 8, (ait & 1) ^ 1);
       tc_fence_after();
+      if (tid == 0 && st < 20) B2L_TRACE(24 + st);
 #pragma unroll
       for (int s = 0; s < G; ++s) {
         if (s < ns) {
@@ -377,11 +392,13 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
         mbar_arrive(bar_w_empty + slot * 8);  // slab bytes are in registers/TMEM: slot may be refilled
         mbar_arrive(bar_a_full + ab * 8);
       }
+      if (tid == 0 && st < 20) B2L_TRACE(44 + st);
     }
 
     // -- epilogue part 1: accumulator -> scaled partial of this rank
     mbar_wait(bar_d_full, 0);
     tc_fence_after();
+    if (tid == 0) B2L_TRACE(104);
     uint32_t acc[16];
     tmem_ld16(tmem_base + lane_base + D_COL, acc);
     const int o = min(nt * TILE_N + tid, p.N - 1);  // padded rows of the last tile are never stored
@@ -396,6 +413,7 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
   // ===================== cross-rank reduction + epilogue (rank 0) =====================
   tc_fence_before();
   if (S > 1) cluster_sync_all(); else __syncthreads();
+  if (tid == 0) B2L_TRACE(105);
   if (rank == 0 && warp < 4) {
     float tot[MAX_M];
     float* part = reinterpret_cast<float*>(smem + L.part);
@@ -438,8 +456,10 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
       }
     }
   }
+  if (tid == 0) B2L_TRACE(106);
   if (S > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (tid == 0) B2L_TRACE(107);
 }
 
 // ---------------------------------------------------------------- re-tiling
@@ -556,6 +576,7 @@ extern "C" int b2l_q4_linear_tc(const b2l_q4_linear_args* a, b2l_stream_t stream
   p.prologue = a->prologue; p.norm_scale = (const __nv_bfloat16*)a->norm_scale; p.eps = a->eps;
   p.epilogue = a->epilogue; p.res = (const __nv_bfloat16*)a->res; p.ldres = a->ldres;
   p.S = S;
+  p.trace = (unsigned long long*)a->trace;
   const int max_slabs = (slabs_total + S - 1) / S;
   p.kseg_max = max_slabs * SLAB_K;
   p.kcb = ((a->flags & B2L_F_ALIAS_N) && a->M <= 8) ? 128 : 256;

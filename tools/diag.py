@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "ops", "model", "bench_layers", "bench_step"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "ops", "model", "trace", "bench_layers", "bench_step"]
 
 
 def rand_q4(N, K, dev, seed=0, sz_dtype=None, groups=1, bits=4):
@@ -342,38 +342,76 @@ def _time(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters * 1e3  # us
 
 
-def sec_bench_layers():
+def make_args(L, x, qt, scales, zeros, N, K, y, *, prologue=0, norm_scale=None, epilogue=0, res=None, split_k=0, flags=0, trace=None):
+    return L.Q4LinearArgs(x=x.data_ptr(), ldx=x.stride(0), qw_tiled=qt.data_ptr(), scales=scales.data_ptr(),
+                          zeros=zeros.data_ptr(), sz_dtype=L.sz_dtype_of(scales), y=y.data_ptr(), ldy=y.stride(0), M=x.shape[0], N=N,
+                          K=K, prologue=prologue, norm_scale=None if norm_scale is None else norm_scale.data_ptr(), eps=1e-5,
+                          epilogue=epilogue, res=None if res is None else res.data_ptr(), ldres=0 if res is None else res.stride(0),
+                          split_k=split_k, flags=flags, trace=None if trace is None else trace.data_ptr())
+
+
+def sec_trace():
+    """clock64 stamps of CTA 0 of one launch: where does a CTA spend its time?"""
     import torch
     from lit_llama_b200 import _lib as L
 
     dev = torch.device("cuda")
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for (name, N, K, S) in [("c_attn", 12288, 4096, 4), ("c_proj", 4096, 4096, 8), ("mlp_proj", 4096, 11008, 8)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=3)
+        qt = tile(L, qw, N, K)
+        x = torch.randn(1, K, device=dev).bfloat16()
+        g = torch.ones(K, device=dev, dtype=torch.bfloat16)
+        y = torch.zeros(1, N, device=dev, dtype=torch.bfloat16)
+        tr = torch.zeros(256, dtype=torch.int64, device=dev)
+        a = make_args(L, x, qt, sc, z, N, K, y, prologue=1, norm_scale=g, split_k=S, trace=tr)
+        for rep in range(2):  # second launch: weights of CTA 0 may be L2-warm, code is warm
+            tr.zero_()
+            flush = torch.empty(200 * 1024 * 1024, dtype=torch.uint8, device=dev).fill_(1)
+            L.check(L.lib().b2l_q4_linear_tc(C.byref(a), L.stream_ptr()), "tc")
+            torch.cuda.synchronize()
+            t = tr.cpu().tolist()
+            t0 = t[0]
+            rel = lambda i: (t[i] - t0) if t[i] else None
+            nst = (K // 32 // S + 1) // 2
+            print(f"{name} S={S} rep={rep} stages={nst}: init_sync={rel(1)} pdl_wait={rel(2)} x_ready={rel(3)} d_full={rel(104)} "
+                  f"csync1={rel(105)} epi={rel(106)} end={rel(107)}")
+            k = min(nst, 20)
+            print("   tma_issue ", [rel(108 + i) for i in range(k)])
+            print("   w_full    ", [rel(4 + i) for i in range(k)])
+            print("   a_empty   ", [rel(24 + i) for i in range(k)])
+            print("   st_done   ", [rel(44 + i) for i in range(k)])
+            print("   a_full@mma", [rel(64 + i) for i in range(k)])
+            print("   commit    ", [rel(84 + i) for i in range(k)])
+            del flush
+
+
+def sec_bench_layers():
+    """GPU time of the int4 linear per 7B shape: `n_copies` launches on distinct weight
+    copies (> L2) captured in one CUDA graph, so the host cost of a launch is not in it."""
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    lib = L.lib()
     for (name, N, K) in [("c_attn", 12288, 4096), ("c_proj", 4096, 4096), ("fc12", 22016, 4096), ("mlp_proj", 4096, 11008), ("lm_head", 32000, 4096)]:
         lv, qw, sc, z = rand_q4(N, K, dev, seed=3)
-        # several copies so that successive calls do not hit L2
-        n_copies = max(2, int(300e6 // (N * K // 2)) + 1)
+        n_copies = max(4, int(400e6 // (N * K // 2)) + 1)
         qts = [tile(L, qw, N, K) for _ in range(n_copies)]
         x = torch.randn(1, K, device=dev).bfloat16()
         y = torch.zeros(1, N, device=dev, dtype=torch.bfloat16)
-        for S in (1, 2, 4, 8):
-            for flags in (0, 2):
-                it = [0]
-
-                def fn():
-                    tc_call(L, x, qts[it[0] % n_copies], sc, z, N, K, y=y, split_k=S, flags=flags)
-                    it[0] += 1
-
-                us = _time(fn, iters=40)
-                gbs = (N * K / 2) / us / 1e3
-                print(f"{name} N={N} K={K} S={S} flags={flags}: {us:.2f} us  {gbs:.0f} GB/s")
-        # generic kernel for comparison
-        yb = torch.zeros(1, N, device=dev, dtype=torch.bfloat16)
-
-        def fg():
-            L.lib().b2l_q_linear(x.data_ptr(), K, qw.data_ptr(), sc.data_ptr(), z.data_ptr(), 0, None, yb.data_ptr(), N, 1, N, K, 4, K, L.stream_ptr())
-
-        us = _time(fg, iters=10)
-        print(f"{name} generic: {us:.2f} us  {(N * K / 2) / us / 1e3:.0f} GB/s")
+        for S in (2, 4, 8):
+            for flags in (0, 1, 3):
+                args = [make_args(L, x, qt, sc, z, N, K, y, split_k=S, flags=flags) for qt in qts]
+                if lib.b2l_q4_linear_tc(C.byref(args[0]), L.stream_ptr()) != 0:
+                    print(f"{name} S={S} flags={flags}: {lib.b2l_last_error().decode()}")
+                    continue
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for a in args:
+                        lib.b2l_q4_linear_tc(C.byref(a), L.stream_ptr())
+                us = _time(g.replay, iters=10, warm=2) / n_copies
+                print(f"{name} N={N} K={K} S={S} flags={flags}: {us:.2f} us/launch  {(N * K / 2) / us / 1e3:.0f} GB/s  ({n_copies} launches/graph)")
         del qts
 
 
