@@ -210,8 +210,10 @@ def time_q4_launches(model, dev):
     a = st.args
     calls = []
 
+    gemv = bool(a.lm_head.qw_mma)
+
     def mk(w, x, ldx, y, ldy, pro, ns, epi, res):
-        return L.Q4LinearArgs(x=x, ldx=ldx, qw_tiled=w.qw_tiled, scales=w.scales, zeros=w.zeros, sz_dtype=a.sz_dtype, y=y, ldy=ldy,
+        return L.Q4LinearArgs(x=x, ldx=ldx, qw_tiled=w.qw_mma if gemv else w.qw_tiled, scales=w.scales, zeros=w.zeros, sz_dtype=a.sz_dtype, y=y, ldy=ldy,
                               M=1, N=w.N, K=w.K, prologue=pro, norm_scale=ns, eps=a.eps, epilogue=epi, res=res, ldres=ldy,
                               split_k=0, flags=0)
 
@@ -225,9 +227,11 @@ def time_q4_launches(model, dev):
     calls.append(mk(a.lm_head, a.x, Cd, a.logits, a.vocab, 1, a.ln_f, 0, None))
     lib, sp = L.lib(), L.stream_ptr()
 
+    fn = lib.b2l_q4_gemv if gemv else lib.b2l_q4_linear_tc
+
     def run():
         for c in calls:
-            rc = lib.b2l_q4_linear_tc(C.byref(c), sp)
+            rc = fn(C.byref(c), sp)
             if rc:
                 raise RuntimeError(lib.b2l_last_error().decode())
 
@@ -241,7 +245,7 @@ def time_q4_launches(model, dev):
         run()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps * 1e-3, len(calls)  # seconds per token's worth of launches
+    return e0.elapsed_time(e1) / reps * 1e-3, len(calls), ("q4_gemv_kernel" if gemv else "q4_linear_tc_kernel")
 
 
 def reduce_max(times, device):
@@ -343,7 +347,7 @@ def main():
             barrier()
             t_e2e = time.perf_counter() - t0
 
-        t_q4, n_q4 = time_q4_launches(model, dev)
+        t_q4, n_q4, q4_name = time_q4_launches(model, dev)
 
     t_dev, t_e2e = reduce_max([t_dev, t_e2e], dev)
 
@@ -374,7 +378,7 @@ def main():
             "e2e": {"value": aggregate_throughput(world, Ke, t_e2e), "unit": "tokens/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 8, "steps": Ke},
             "gpu_launches": launches * K,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "kernel": "q4_linear_tc_kernel", "launches_per_token": n_q4, "bytes_per_token_launches": W,
+                         "kernel": q4_name, "launches_per_token": n_q4, "bytes_per_token_launches": W,
                          "peak_source": which,
                          "whole_token": {"bytes": bytes_per_token, "achieved": bytes_per_token * K / t_dev / 1e9,
                                          "frac": bytes_per_token * K / t_dev / 1e9 / peak}},

@@ -100,7 +100,7 @@ typedef struct b2l_q4_linear_args {
   int epilogue;         /* B2L_EPI_*                                                  */
   const void* res;      /* bf16 [M, N] residual (leading dim ldres) for RESIDUAL      */
   int ldres;
-  int split_k;          /* cluster size along K: 1,2,4,8 (0 = library picks)          */
+  int split_k;          /* cluster size along K: 1..8 (0 = library picks)             */
   int flags;            /* B2L_F_*                                                    */
   void* trace;          /* debug: device uint64[256] receiving clock64() stamps of CTA 0
                            (NULL = off); see tools/diag.py `trace`                     */
@@ -108,9 +108,10 @@ typedef struct b2l_q4_linear_args {
 
 enum {
   B2L_F_PDL = 1,        /* launch with programmatic dependent launch                   */
-  B2L_F_ALIAS_N = 2,    /* B operand rows 8..15 alias rows 0..7 (M <= 8)               */
-  B2L_F_ROPE_ROWS = 4   /* b2l_attention: `rope` holds the T rows already selected by
+  B2L_F_NO_ALIAS_N = 2, /* debug: do not alias B operand rows 8..15 onto rows 0..7     */
+  B2L_F_ROPE_ROWS = 4,  /* b2l_attention: `rope` holds the T rows already selected by
                            input_pos (the reference's call convention, model.py:93)    */
+  B2L_F_ATTN_UNFUSED = 8 /* debug: force the three-kernel attention path for T == 1    */
 };
 
 /* Fused [RMSNorm ->] int4 linear [-> residual | SwiGLU] on tcgen05.  Replaces
@@ -118,6 +119,17 @@ enum {
  * (quantization.py:413-423) + the residual add / silu*mul of Block/MLP.forward
  * (model.py:166-167, 252). */
 int b2l_q4_linear_tc(const b2l_q4_linear_args* args, b2l_stream_t stream);
+
+/* Batch-1 decode variant of the fused linear (M == 1): TMA-staged packed weights, PDL
+ * prefetch, warp-synchronous mma.sync contraction from registers, persistent CTAs that own
+ * 16-row blocks over the full K (no cross-CTA reduction, deterministic).  Same argument
+ * block as b2l_q4_linear_tc (ldx/ldy/ldres unused; split_k > 0 overrides the grid size);
+ * qw_tiled must come from b2l_q4_tile_mma: [N/16 row blocks][K/64 k blocks][32 lanes][16 B].
+ * For B2L_EPI_SWIGLU the rows of a 16-row block are [8 of c_fc1 | 8 of c_fc2]. */
+size_t b2l_q4_tiled_mma_bytes(int N, int K);
+int b2l_q4_tile_mma(const void* qw, void* qw_tiled, int N, int K, b2l_stream_t stream);
+int b2l_q4_untile_mma(const void* qw_tiled, void* qw, int N, int K, b2l_stream_t stream);
+int b2l_q4_gemv(const b2l_q4_linear_args* args, b2l_stream_t stream);
 
 /* ------------------------------------------------------------------------------
  * model.py element-wise pieces (used by the module-level drop-ins and by prefill)
@@ -151,7 +163,8 @@ int b2l_add(const void* a, const void* b, void* y, size_t n, b2l_stream_t stream
  *            k,v at logical slot min(input_pos[t], S-1) and attends slots <= that.
  * ring_start int32 [1] on the device, read-only here; b2l_ring_advance moves it
  * y     bf16 [B, T, C]
- * work  f32 scratch of b2l_attn_workspace_bytes(...) for split-S partials
+ * work  scratch of b2l_attn_workspace_bytes(...) bytes (split-S partials + tickets);
+ *       the caller zero-fills it ONCE after allocating it
  * ---------------------------------------------------------------------------- */
 size_t b2l_attn_workspace_bytes(int B, int n_head, int head_size, int T, int S);
 int b2l_attention(void* qkv, void* k_cache, void* v_cache, const void* rope,
@@ -180,7 +193,8 @@ int b2l_kv_unroll(const void* cache, const int32_t* ring_start, void* out, int B
  * every kernel of the step enqueued by one call.
  * ---------------------------------------------------------------------------- */
 typedef struct b2l_q4_weight {
-  const void* qw_tiled;
+  const void* qw_tiled;   /* b2l_q4_tile layout (tcgen05 kernel), used when B > 1; may be NULL if B == 1 */
+  const void* qw_mma;     /* b2l_q4_tile_mma layout (batch-1 kernel), used when B == 1; may be NULL if B > 1 */
   const void* scales;
   const void* zeros;
   int N, K;
@@ -191,7 +205,9 @@ typedef struct b2l_layer {
   const void* rms_2;       /* bf16 [C] */
   b2l_q4_weight c_attn;    /* [3C, C]                                                */
   b2l_q4_weight c_proj;    /* [C, C]                                                 */
-  b2l_q4_weight c_fc12;    /* [2*n_hidden, C], rows interleaved 64/64 per tile       */
+  b2l_q4_weight c_fc12;    /* [2*n_hidden, C]; qw_tiled rows interleaved 64/64 per 128-row tile,
+                              qw_mma rows interleaved 8/8 per 16-row block (scales/zeros in the
+                              order of the layout in use)                               */
   b2l_q4_weight mlp_proj;  /* [C, n_hidden]                                          */
   void* k_cache;           /* bf16 [B, nh, S, hs]                                    */
   void* v_cache;
@@ -224,6 +240,12 @@ typedef struct b2l_decode_args {
 int b2l_decode_step(const b2l_decode_args* args, b2l_stream_t stream);
 /* Number of kernels one b2l_decode_step enqueues (for bench.py's gpu_launches). */
 int b2l_decode_step_launches(const b2l_decode_args* args);
+
+/* Debug only (tools/diag.py): tcgen05.mma issue / completion cycle counts of one CTA.
+ * out: device uint64[rounds*3] = {cycles to issue n_mma MMAs, cycles to issue the commit,
+ * cycles until the commit's mbarrier arrives}. */
+int b2l_debug_mma_rate(void* out, int n_mma, int n_acc, int a_from_smem, int rounds,
+                       b2l_stream_t stream);
 
 #ifdef __cplusplus
 }

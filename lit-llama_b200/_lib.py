@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libb200llama.so")
 B2L_BF16, B2L_F32 = 0, 1
 PRO_NONE, PRO_RMSNORM = 0, 1
 EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU = 0, 1, 2
-F_PDL, F_ALIAS_N = 1, 2
+F_PDL, F_NO_ALIAS_N, F_ROPE_ROWS = 1, 2, 4
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -30,7 +30,7 @@ class Q4LinearArgs(C.Structure):
 
 
 class Q4Weight(C.Structure):
-    _fields_ = [("qw_tiled", c_void_p), ("scales", c_void_p), ("zeros", c_void_p), ("N", c_int), ("K", c_int)]
+    _fields_ = [("qw_tiled", c_void_p), ("qw_mma", c_void_p), ("scales", c_void_p), ("zeros", c_void_p), ("N", c_int), ("K", c_int)]
 
 
 class Layer(C.Structure):
@@ -65,6 +65,10 @@ _SIGS = {
     "b2l_q4_tile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b2l_q4_untile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b2l_q4_linear_tc": (c_int, [C.POINTER(Q4LinearArgs), c_void_p]),
+    "b2l_q4_tiled_mma_bytes": (c_size_t, [c_int, c_int]),
+    "b2l_q4_tile_mma": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "b2l_q4_untile_mma": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "b2l_q4_gemv": (c_int, [C.POINTER(Q4LinearArgs), c_void_p]),
     "b2l_rmsnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "b2l_embedding": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2l_silu_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -77,6 +81,7 @@ _SIGS = {
     "b2l_kv_unroll": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2l_decode_step": (c_int, [C.POINTER(DecodeArgs), c_void_p]),
     "b2l_decode_step_launches": (c_int, [C.POINTER(DecodeArgs)]),
+    "b2l_debug_mma_rate": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)

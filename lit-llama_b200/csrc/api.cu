@@ -63,19 +63,26 @@ static int q4_call(const b2l_q4_weight& w, const void* x, int ldx, void* y, int 
                    b2l_stream_t stream) {
   b2l_q4_linear_args a{};
   a.x = x; a.ldx = ldx;
-  a.qw_tiled = w.qw_tiled; a.scales = w.scales; a.zeros = w.zeros; a.sz_dtype = sz_dtype;
+  const bool gemv = (M == 1 && w.qw_mma != nullptr);
+  a.qw_tiled = gemv ? w.qw_mma : w.qw_tiled; a.scales = w.scales; a.zeros = w.zeros; a.sz_dtype = sz_dtype;
   a.y = y; a.ldy = ldy;
   a.M = M; a.N = w.N; a.K = w.K;
   a.prologue = prologue; a.norm_scale = norm_scale; a.eps = eps;
   a.epilogue = epilogue; a.res = res; a.ldres = ldres;
   a.split_k = 0;
   a.flags = flags;
+  if (gemv) return b2l_q4_gemv(&a, stream);
+  if (a.qw_tiled == nullptr) {
+    set_error("b2l_decode_step: weight has no tiling for batch %d", M);
+    return B2L_E_STATE;
+  }
   return b2l_q4_linear_tc(&a, stream);
 }
 
 extern "C" int b2l_decode_step_launches(const b2l_decode_args* d) {
   if (!d) return 0;
-  return 2 + d->n_layer * 7 + 1;  // embedding + ring advance, 7 per Block, ln_f+lm_head
+  const int attn = (d->n_embd / d->n_head == 128) ? 1 : 3;  // fused single-token attention for head_size 128
+  return 2 + d->n_layer * (4 + attn) + 1;  // ring advance + embedding, per Block 4 linears + attention, ln_f+lm_head
 }
 
 extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {

@@ -197,6 +197,216 @@ __global__ void kv_unroll_kernel(const __nv_bfloat16* __restrict__ cache, const 
   for (int d = threadIdx.x; d < hs; d += blockDim.x) dst[d] = src[d];
 }
 
+// ----------------------------------------------------------------------------------
+// Fused single-token attention for head_size 128 (every LLaMA size): one kernel does
+// RoPE(q), RoPE(k) + in-place KV append, split-S online-softmax attention over the valid
+// slots, and the cross-split merge (last CTA of a head, atomic ticket).
+//
+// grid (B*n_head, n_split), 4 warps.  A warp handles 4 keys per iteration: 8 lanes per key,
+// 16 head dims (32 B) per lane, so a K/V row is read with two 16-byte loads per lane and a
+// score needs 3 shuffles.  Under PDL the CTA prefetches its K/V chunk into L2 before it
+// waits for the c_attn kernel (old cache rows do not depend on the current token).
+// ----------------------------------------------------------------------------------
+constexpr int FD_CHUNK = 128;   // keys per CTA
+constexpr int FD_WARPS = 4;
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+__global__ void __launch_bounds__(FD_WARPS * 32)
+    attn_decode_fused_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ k_cache,
+                             __nv_bfloat16* __restrict__ v_cache, const float* __restrict__ rope,
+                             const int64_t* __restrict__ input_pos, const int32_t* __restrict__ ring_start,
+                             __nv_bfloat16* __restrict__ y, float* __restrict__ work, int* __restrict__ tickets,
+                             int n_head, int S, int block_size, int n_split) {
+  constexpr int HS = 128;
+  const int bh = blockIdx.x, b = bh / n_head, h = bh % n_head, sp = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = n_head * HS;
+  const size_t head_base = ((size_t)b * n_head + h) * S * HS;
+
+  // ---- before the dependency: pull this CTA's slice of the cache towards L2 (worst-case range)
+  {
+    const int j0 = sp * FD_CHUNK;
+    const int nrows = min(FD_CHUNK, S - j0);
+    // physical rows are the logical ones rotated by the ring; prefetching the unrotated range is a
+    // hint only (exact when the ring has not started, i.e. always before the cache is full)
+    for (int i = threadIdx.x; i < nrows * 2; i += blockDim.x) {
+      const char* pk = reinterpret_cast<const char*>(k_cache + head_base + (size_t)(j0 + (i >> 1)) * HS) + (i & 1) * 128;
+      const char* pv = reinterpret_cast<const char*>(v_cache + head_base + (size_t)(j0 + (i >> 1)) * HS) + (i & 1) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pk));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pv));
+    }
+  }
+  pdl_wait();
+  pdl_launch_dependents();  // attn.c_proj may start streaming its weights
+
+  const long long p = input_pos[0];
+  const int w_slot = (int)(p < S ? p : (long long)S - 1);  // logical slot of the new token
+  const int L = w_slot + 1;                                 // valid logical slots 0..L-1
+  const int n_active = (L + FD_CHUNK - 1) / FD_CHUNK;
+  if (sp >= n_active) return;
+  const int ring = *ring_start;
+  const long long prow = p < block_size ? p : (long long)block_size - 1;
+  const int j0 = sp * FD_CHUNK, j1 = min(L, j0 + FD_CHUNK);
+
+  const int grp = lane >> 3, sub = lane & 7, d0 = sub * 16;
+  // rope row for this lane's 8 pairs
+  float cs[16];
+  {
+    const float4* rp = reinterpret_cast<const float4*>(rope + ((size_t)prow * (HS / 2) + d0 / 2) * 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 t = rp[i];
+      cs[4 * i] = t.x; cs[4 * i + 1] = t.y; cs[4 * i + 2] = t.z; cs[4 * i + 3] = t.w;
+    }
+  }
+  const __nv_bfloat16* qrow = qkv + (size_t)b * 3 * C + h * HS + d0;
+  float q[16];
+  {
+    float raw[16];
+    bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow), raw);
+    bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + 8), raw + 8);
+    const float scale = rsqrtf((float)HS);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float c = cs[2 * i], s_ = cs[2 * i + 1];
+      const float e = rbf(__fsub_rn(__fmul_rn(raw[2 * i], c), __fmul_rn(raw[2 * i + 1], s_)));
+      const float o = rbf(__fadd_rn(__fmul_rn(raw[2 * i + 1], c), __fmul_rn(raw[2 * i], s_)));
+      q[2 * i] = e * scale;
+      q[2 * i + 1] = o * scale;
+    }
+  }
+  // the CTA whose chunk holds the new slot appends k (rotated) and v
+  if (w_slot >= j0 && w_slot < j1) {
+    if (warp == 0 && grp == 0) {
+      int phys = w_slot + ring; if (phys >= S) phys -= S;
+      float raw[16];
+      bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + C), raw);
+      bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + C + 8), raw + 8);
+      uint32_t out[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float c = cs[2 * i], s_ = cs[2 * i + 1];
+        const float e = __fsub_rn(__fmul_rn(raw[2 * i], c), __fmul_rn(raw[2 * i + 1], s_));
+        const float o = __fadd_rn(__fmul_rn(raw[2 * i + 1], c), __fmul_rn(raw[2 * i], s_));
+        out[i] = (__float_as_uint(rbf(e)) >> 16) | (__float_as_uint(rbf(o)) & 0xffff0000u);
+      }
+      uint4* kd = reinterpret_cast<uint4*>(k_cache + head_base + (size_t)phys * HS + d0);
+      kd[0] = make_uint4(out[0], out[1], out[2], out[3]);
+      kd[1] = make_uint4(out[4], out[5], out[6], out[7]);
+      const uint4* vs = reinterpret_cast<const uint4*>(qrow + 2 * C);
+      uint4* vd = reinterpret_cast<uint4*>(v_cache + head_base + (size_t)phys * HS + d0);
+      vd[0] = vs[0];
+      vd[1] = vs[1];
+    }
+    __syncthreads();  // the appended row is read below by this CTA
+  }
+
+  float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int jj = j0 + warp * 4; jj < j1; jj += FD_WARPS * 4) {  // warp-uniform trip count
+    const int j = jj + grp;
+    const bool valid = j < j1;
+    int phys = (valid ? j : j1 - 1) + ring; if (phys >= S) phys -= S;
+    const uint4* kr = reinterpret_cast<const uint4*>(k_cache + head_base + (size_t)phys * HS + d0);
+    const uint4* vr = reinterpret_cast<const uint4*>(v_cache + head_base + (size_t)phys * HS + d0);
+    const uint4 k0 = kr[0], k1 = kr[1], v0 = vr[0], v1 = vr[1];
+    float kf[16], vf[16];
+    bf16x8_to_f32(k0, kf); bf16x8_to_f32(k1, kf + 8);
+    float sc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sc = fmaf(q[i], kf[i], sc);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+    if (valid) {
+      bf16x8_to_f32(v0, vf); bf16x8_to_f32(v1, vf + 8);
+      const float mn = fmaxf(m, sc);
+      const float corr = __expf(m - mn), pj = __expf(sc - mn);
+      l = l * corr + pj;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(pj, vf[i], acc[i] * corr);
+      m = mn;
+    }
+  }
+  // merge the 4 key groups of the warp (lanes with the same `sub` hold the same dims)
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+    const float lo = __shfl_xor_sync(0xffffffffu, l, off);
+    const float mn = fmaxf(m, mo);
+    const float ca = (m == -INFINITY) ? 0.f : __expf(m - mn);
+    const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+    l = l * ca + lo * cb;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float ao = __shfl_xor_sync(0xffffffffu, acc[i], off);
+      acc[i] = acc[i] * ca + ao * cb;
+    }
+    m = mn;
+  }
+  // merge the warps through shared memory
+  __shared__ float sm_m[FD_WARPS], sm_l[FD_WARPS];
+  __shared__ float sm_acc[FD_WARPS][HS];
+  __shared__ int sm_last;
+  if (lane == 0) { sm_m[warp] = m; sm_l[warp] = l; }
+  if (grp == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sm_acc[warp][d0 + i] = acc[i];
+  }
+  __syncthreads();
+  float M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < FD_WARPS; ++w) M = fmaxf(M, sm_m[w]);
+  float wgt[FD_WARPS], Ls = 0.f;
+#pragma unroll
+  for (int w = 0; w < FD_WARPS; ++w) {
+    wgt[w] = (sm_m[w] == -INFINITY) ? 0.f : __expf(sm_m[w] - M);
+    Ls += sm_l[w] * wgt[w];
+  }
+  const int d = threadIdx.x;  // 128 threads == HS
+  float a = 0.f;
+#pragma unroll
+  for (int w = 0; w < FD_WARPS; ++w) a += sm_acc[w][d] * wgt[w];
+
+  if (n_active == 1) {  // nothing to merge
+    y[(size_t)b * C + h * HS + d] = f2bf(a / Ls);
+    return;
+  }
+  float* out = work + ((size_t)bh * n_split + sp) * (HS + 2);
+  if (d == 0) { out[0] = M; out[1] = Ls; }
+  out[2 + d] = a;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(&tickets[bh], 1);
+    sm_last = (t == n_active - 1);
+    if (sm_last) tickets[bh] = 0;  // every contributor has arrived: safe to re-arm for the next step
+  }
+  __syncthreads();
+  if (!sm_last) return;
+  __threadfence();
+  const float* base = work + (size_t)bh * n_split * (HS + 2);
+  float MM = -INFINITY;
+  for (int s2 = 0; s2 < n_active; ++s2) MM = fmaxf(MM, __ldcg(base + (size_t)s2 * (HS + 2)));
+  float LL = 0.f, aa = 0.f;
+  for (int s2 = 0; s2 < n_active; ++s2) {
+    const float ms = __ldcg(base + (size_t)s2 * (HS + 2));
+    const float wg = __expf(ms - MM);
+    LL += __ldcg(base + (size_t)s2 * (HS + 2) + 1) * wg;
+    aa += __ldcg(base + (size_t)s2 * (HS + 2) + 2 + d) * wg;
+  }
+  y[(size_t)b * C + h * HS + d] = f2bf(aa / LL);
+}
+
 static inline void split_plan(int T, int S, int* n_split, int* chunk) {
   if (T > 1) { *n_split = 1; *chunk = S; return; }
   *chunk = 64;
@@ -222,10 +432,18 @@ static int launch_attn(const __nv_bfloat16* qkv, KvView kv, const int64_t* input
 
 using namespace b2l;
 
-extern "C" size_t b2l_attn_workspace_bytes(int B, int n_head, int head_size, int T, int S) {
+static inline size_t ws_partials_bytes(int B, int n_head, int head_size, int T, int S) {
   int n_split, chunk;
   split_plan(T, S, &n_split, &chunk);
-  return (size_t)B * n_head * T * n_split * (head_size + 2) * sizeof(float);
+  size_t a = (size_t)B * n_head * T * n_split * (head_size + 2) * sizeof(float);
+  size_t f = (size_t)B * n_head * ((S + FD_CHUNK - 1) / FD_CHUNK) * (head_size + 2) * sizeof(float);
+  return ((a > f ? a : f) + 15) & ~(size_t)15;
+}
+
+// [partials | int32 tickets[B*n_head]].  The caller zero-fills the buffer once when it
+// allocates it; the fused decode kernel re-arms its tickets itself.
+extern "C" size_t b2l_attn_workspace_bytes(int B, int n_head, int head_size, int T, int S) {
+  return ws_partials_bytes(B, n_head, head_size, T, S) + (size_t)B * n_head * sizeof(int);
 }
 
 extern "C" int b2l_ring_advance(const int64_t* input_pos, int T, int32_t* ring_start, int S, b2l_stream_t stream) {
@@ -244,6 +462,15 @@ extern "C" int b2l_attention(void* qkv, void* k_cache, void* v_cache, const void
   B2L_CHECK_SUPPORTED(head_size % 2 == 0 && head_size >= 2 && head_size <= 32 * ATT_MAX_EPL,
                       "b2l_attention: head_size %d unsupported (even, <= %d)", head_size, 32 * ATT_MAX_EPL);
   cudaStream_t st = (cudaStream_t)stream;
+  if (T == 1 && head_size == 128 && !(flags & B2L_F_ROPE_ROWS) && !(flags & B2L_F_ATTN_UNFUSED)) {
+    const int n_split = (S + FD_CHUNK - 1) / FD_CHUNK;
+    int* tickets = reinterpret_cast<int*>(reinterpret_cast<char*>(work) + ws_partials_bytes(B, n_head, head_size, T, S));
+    LaunchCfg lc(dim3(B * n_head, n_split), dim3(FD_WARPS * 32), 0, st, (flags & B2L_F_PDL) != 0);
+    B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, attn_decode_fused_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_cache,
+                                (__nv_bfloat16*)v_cache, (const float*)rope, input_pos, ring_start, (__nv_bfloat16*)y,
+                                (float*)work, tickets, n_head, S, block_size, n_split));
+    return 0;
+  }
   int rt = head_size / 2 < 32 ? 32 : head_size / 2;
   rope_append_kernel<<<dim3(B * T, n_head), rt, 0, st>>>((__nv_bfloat16*)qkv, (__nv_bfloat16*)k_cache,
                                                         (__nv_bfloat16*)v_cache, (const float*)rope, input_pos,

@@ -1,0 +1,449 @@
+// Batch-1 decode kernel: fused [RMSNorm ->] int4 weight-only GEMV [-> residual | SwiGLU].
+//
+// Replaces, for gptq.int4 with one (scale, zero) per output row and a single activation row:
+//   ColBlockQuantizedLinear.forward      lit_llama/quantization.py:413-423
+//   linear_kernel_4bit_weight (Triton)   lit_llama/quantization.py:187-333
+//   RMSNorm.forward                      lit_llama/model.py:270-277      (prologue)
+//   x + h / silu(a) * b                  lit_llama/model.py:166-167, 252 (epilogue)
+//
+// Why not tcgen05 here: measured on B200 (tools/diag.py mma_rate / trace)
+// a single thread issues a 128x16x16 tcgen05.mma every 45-80 cycles and every
+// convert -> commit -> mbarrier round trip costs 300-500 cycles, so at one activation row the
+// tensor-memory path is latency-bound at ~1/5 of HBM speed.  This kernel keeps the
+// Blackwell data movement (TMA bulk copies into an mbarrier ring, PDL prefetch of the weights
+// ahead of the dependency) and runs the tiny contraction warp-synchronously with
+// mma.sync.m16n8k16 from registers: no TMEM hand-offs, no cross-CTA reduction.
+//
+// Work split: a persistent CTA owns 16-row blocks rb = cta, cta + grid, ... over the FULL K
+// (so nothing is reduced across CTAs and the result is deterministic).  The 8 consumer warps
+// split K inside a stage; their fp32 partials meet in shared memory, where the epilogue warp
+// applies y = scale * (acc - (128 + zero) * sum(x)) and the fused epilogue.
+//
+// Weight layout (b2l_q4_tile_mma): [N/16 row blocks][K/64 k blocks][32 lanes][16 B].  Word c of
+// lane (g = lane/4, t = lane%4) holds the A fragment of k16 chunk c: nibble s (s < 4) is row
+// g + 8*(s&1), k = 64*kb + 16*c + 2*t + 8*(s>>1); nibble s+4 is the same row at k+1.  So
+// ((w >> 4s) & 0x000f000f) | 0x43004300 is register a_s of mma.m16n8k16 as bf16 (128 + level).
+#include "b2l_common.cuh"
+
+namespace b2l {
+namespace q4mv {
+
+constexpr int RB = 16;                        // rows per row block
+constexpr int KB = 64;                        // k per k block (4 MMAs)
+constexpr int KB_BYTES = 512;                 // one (row block, k block): 32 lanes x 16 B
+constexpr int NCW = 8;                        // consumer warps
+constexpr int KB_PER_STAGE = 32;              // 16 KB per stage, 4 k blocks per warp
+constexpr int STAGE_BYTES = KB_PER_STAGE * KB_BYTES;
+constexpr int MAX_STAGES = 6;
+constexpr int PRODUCER_WARP = NCW;            // warp 8
+constexpr int NTHREADS = (NCW + 2) * 32;      // 320
+
+struct Params {
+  const __nv_bfloat16* x;
+  const uint8_t* qwt;
+  const void* scales; const void* zeros; int szdt;
+  __nv_bfloat16* y;
+  int N, K;              // N rows (padded to a multiple of 16 in the tiled weight), K % 64 == 0
+  int n_rb;              // row blocks
+  int prologue; const __nv_bfloat16* norm_scale; float eps;
+  int epilogue; const __nv_bfloat16* res;
+  int nst;               // ring stages
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(mbar)
+      : "memory");
+}
+// barrier ids are immediates so that ptxas reserves only the 8 barriers this kernel uses
+template <int ID> __device__ __forceinline__ void bar_sync_c(int n) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
+template <int ID> __device__ __forceinline__ void bar_arrive_c(int n) { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  switch (id) {
+    case 1: bar_sync_c<1>(n); break;
+    case 3: bar_sync_c<3>(n); break;
+    case 4: bar_sync_c<4>(n); break;
+    case 5: bar_sync_c<5>(n); break;
+    case 6: bar_sync_c<6>(n); break;
+    default: bar_sync_c<7>(n); break;
+  }
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int n) {
+  switch (id) {
+    case 4: bar_arrive_c<4>(n); break;
+    case 5: bar_arrive_c<5>(n); break;
+    case 6: bar_arrive_c<6>(n); break;
+    default: bar_arrive_c<7>(n); break;
+  }
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// shared memory map
+struct SmemLayout {
+  uint32_t ring, xf, scratch, red, bars, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int nst, int K) {
+  SmemLayout L;
+  uint32_t o = 0;
+  L.ring = o;    o += (uint32_t)nst * STAGE_BYTES;
+  L.xf = o;      o += (uint32_t)(K / KB) * 128;       // B fragments: [k block][t (4)][32 B]
+  L.scratch = o; o += 2 * NCW * RB * 4;               // [buf][warp][row] fp32 partials
+  L.red = o;     o += 64;                             // per-warp reduction scratch + sum(x)
+  o = (o + 7u) & ~7u;
+  L.bars = o;    o += 2 * MAX_STAGES * 8;
+  L.total = (o + 127u) & ~127u;
+  return L;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const SmemLayout L = smem_layout(p.nst, p.K);
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_kb = p.K / KB;                                           // k blocks per row block
+  const int stages_per_rb = (n_kb + KB_PER_STAGE - 1) / KB_PER_STAGE;  // last stage of a row block may be short
+  const int my_rbs = (p.n_rb > (int)blockIdx.x) ? (p.n_rb - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total_stages = my_rbs * stages_per_rb;
+  const uint32_t bar_full = sbase + L.bars, bar_empty = bar_full + MAX_STAGES * 8;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.nst; ++i) {
+      mbar_init(bar_full + i * 8, 1);
+      mbar_init(bar_empty + i * 8, NCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == PRODUCER_WARP) {
+    // ===================== TMA producer: the CTA's row blocks, stage by stage =====================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 1;  // fresh barriers: waiting on parity 1 passes immediately
+      int it = 0;
+      for (int r = 0; r < my_rbs; ++r) {
+        const int rb = blockIdx.x + r * gridDim.x;
+        const uint8_t* src = p.qwt + (size_t)rb * n_kb * KB_BYTES;
+        for (int s = 0; s < stages_per_rb; ++s, ++it) {
+          const int nkb = min(KB_PER_STAGE, n_kb - s * KB_PER_STAGE);
+          const uint32_t bytes = (uint32_t)nkb * KB_BYTES;
+          mbar_wait(bar_empty + slot * 8, phase);
+          mbar_expect_tx(bar_full + slot * 8, bytes);
+          tma_bulk_g2s(sbase + L.ring + slot * STAGE_BYTES, src + (size_t)s * STAGE_BYTES, bytes, bar_full + slot * 8);
+          if (++slot == p.nst) { slot = 0; phase ^= 1; }
+          if (it + 1 == min(total_stages, p.nst)) pdl_launch_dependents();  // ring full: next kernel may prefetch
+        }
+      }
+      if (total_stages == 0) pdl_launch_dependents();
+    }
+  } else if (warp < NCW) {
+    // ===================== consumer warps =====================
+    pdl_wait();
+    float* red = reinterpret_cast<float*>(smem + L.red);
+    // ---- activations: [RMSNorm], B-fragment order, sum(x)
+    {
+      const bool norm = (p.prologue == B2L_PRO_RMSNORM);
+      constexpr int NT = NCW * 32;   // 256 threads, 8 elements each per pass
+      constexpr int MAXC = 6;        // up to 12288 elements in registers
+      uint4 xv[MAXC], gv[MAXC];
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int k = (c * NT + tid) * 8;
+        xv[c] = make_uint4(0, 0, 0, 0);
+        gv[c] = make_uint4(0, 0, 0, 0);
+        if (k < p.K) {
+          xv[c] = *reinterpret_cast<const uint4*>(p.x + k);
+          if (norm) gv[c] = *reinterpret_cast<const uint4*>(p.norm_scale + k);
+        }
+      }
+      float rinv = 1.f;
+      if (norm) {
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          const uint32_t w[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float a = __uint_as_float(w[q] << 16), b = __uint_as_float(w[q] & 0xffff0000u);
+            ss += rbf(a * a) + rbf(b * b);
+          }
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+        named_bar_sync(1, NT);
+        ss = 0.f;
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) ss += red[w];
+        rinv = rms_rinv(ss, p.K, p.eps);
+        named_bar_sync(1, NT);
+      }
+      float sx = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int k = (c * NT + tid) * 8;
+        if (k < p.K) {
+          uint32_t w[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+          if (norm) {
+            const uint32_t g[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float a = rms_apply(__uint_as_float(w[q] << 16), rinv, __uint_as_float(g[q] << 16));
+              const float b = rms_apply(__uint_as_float(w[q] & 0xffff0000u), rinv, __uint_as_float(g[q] & 0xffff0000u));
+              sx += a + b;
+              w[q] = (__float_as_uint(a) >> 16) | (__float_as_uint(b) & 0xffff0000u);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sx += __uint_as_float(w[q] << 16) + __uint_as_float(w[q] & 0xffff0000u);
+          }
+          // 8 consecutive k = half of a k16 chunk: pair q (k = k0 + 2q, +1) is B register (half) of lane t = q
+          // xf[k block][t][chunk c16 (4)][half (2)] u32
+          const int kb = k >> 6, c16 = (k >> 4) & 3, half = (k >> 3) & 1;
+          uint32_t* dst = reinterpret_cast<uint32_t*>(smem + L.xf + kb * 128);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q * 8 + c16 * 2 + half] = w[q];
+        }
+      }
+      sx = warp_sum(sx);
+      if (lane == 0) red[8 + warp] = sx;
+      named_bar_sync(1, NT);
+      if (tid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) t += red[8 + w];
+        red[7 + 9] = t;  // red[16]: sum over K of the (normalised) activations
+      }
+      named_bar_sync(3, NT + 32);  // releases the epilogue warp too: xf and sum(x) are ready
+    }
+
+    // ---- weights: stage -> registers -> mma.sync
+    const int t4 = lane & 3;
+    int slot = 0;
+    uint32_t phase = 0;
+    float* scratch = reinterpret_cast<float*>(smem + L.scratch);
+    for (int r = 0; r < my_rbs; ++r) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};  // two independent mma chains
+      for (int s = 0; s < stages_per_rb; ++s) {
+        const int nkb = min(KB_PER_STAGE, n_kb - s * KB_PER_STAGE);
+        mbar_wait(bar_full + slot * 8, phase);
+        const uint8_t* st_base = smem + L.ring + slot * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < KB_PER_STAGE / NCW; ++i) {
+          const int kbl = i * NCW + warp;  // k block inside the stage
+          if (kbl < nkb) {
+            const uint4 wv = *reinterpret_cast<const uint4*>(st_base + kbl * KB_BYTES + lane * 16);
+            const uint4* xp = reinterpret_cast<const uint4*>(smem + L.xf + (s * KB_PER_STAGE + kbl) * 128 + t4 * 32);
+            const uint4 xa = xp[0], xb = xp[1];
+            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+            const uint32_t bb[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t a[4];
+              a[0] = (ww[c] & 0x000f000fu) | 0x43004300u;
+              a[1] = ((ww[c] >> 4) & 0x000f000fu) | 0x43004300u;
+              a[2] = ((ww[c] >> 8) & 0x000f000fu) | 0x43004300u;
+              a[3] = ((ww[c] >> 12) & 0x000f000fu) | 0x43004300u;
+              if (c & 1) mma_bf16_16816(acc1, a, bb[2 * c], bb[2 * c + 1]);
+              else mma_bf16_16816(acc, a, bb[2 * c], bb[2 * c + 1]);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + slot * 8);
+        if (++slot == p.nst) { slot = 0; phase ^= 1; }
+      }
+      // column 0 of the 16x8 result: lanes with t == 0 hold rows g (acc[0]) and g + 8 (acc[2])
+      const int buf = r & 1;
+      named_bar_sync(4 + buf, NCW * 32 + 32);  // epilogue warp has drained this scratch buffer (two row blocks ago)
+      if (t4 == 0) {
+        scratch[(buf * NCW + warp) * RB + (lane >> 2)] = acc[0] + acc1[0];
+        scratch[(buf * NCW + warp) * RB + (lane >> 2) + 8] = acc[2] + acc1[2];
+      }
+      __syncwarp();
+      named_bar_arrive(6 + buf, NCW * 32 + 32);  // partials of this row block are in the scratch buffer
+    }
+  } else {
+    // ===================== epilogue warp =====================
+    pdl_wait();
+    const float* red = reinterpret_cast<const float*>(smem + L.red);
+    const float* scratch = reinterpret_cast<const float*>(smem + L.scratch);
+    named_bar_sync(3, NCW * 32 + 32);
+    const float sumx = red[16];
+    // both scratch buffers start free
+    named_bar_arrive(4, NCW * 32 + 32);
+    if (my_rbs > 1) named_bar_arrive(5, NCW * 32 + 32);
+    for (int r = 0; r < my_rbs; ++r) {
+      const int rb = blockIdx.x + r * gridDim.x;
+      const int buf = r & 1;
+      const int row = lane & 15;
+      const int o = min(rb * RB + row, p.N - 1);
+      const float sc = load_sz(p.scales, p.szdt, o);
+      const float zz = 128.0f + load_sz(p.zeros, p.szdt, o);
+      float resv = 0.f;
+      if (p.epilogue == B2L_EPI_RESIDUAL && lane < 16 && rb * RB + row < p.N) resv = bf2f(p.res[rb * RB + row]);
+      named_bar_sync(6 + buf, NCW * 32 + 32);
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NCW; ++w) t += scratch[(buf * NCW + w) * RB + row];  // fixed order: deterministic
+      if (r + 2 < my_rbs) named_bar_arrive(4 + buf, NCW * 32 + 32);               // scratch buffer free again
+      const float v = rbf(sc * (t - zz * sumx));
+      if (p.epilogue == B2L_EPI_SWIGLU) {
+        // rows 0..7 of the block are c_fc1[o..o+7], rows 8..15 are c_fc2[o..o+7]
+        const float b = __shfl_down_sync(0xffffffffu, v, 8);
+        if (lane < 8) {
+          const float sl = rbf(v / (1.0f + expf(-v)));
+          p.y[rb * 8 + lane] = f2bf(sl * b);
+        }
+      } else if (lane < 16 && rb * RB + row < p.N) {
+        p.y[rb * RB + row] = f2bf(p.epilogue == B2L_EPI_RESIDUAL ? v + resv : v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- re-tiling for the mma.sync layout
+__global__ void q4_tile_mma_kernel(const uint8_t* __restrict__ qw, uint32_t* __restrict__ out, int N, int K) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one output word
+  const int n_kb = K / KB;
+  const int n_rb = (N + RB - 1) / RB;
+  const size_t total = (size_t)n_rb * n_kb * 32 * 4;
+  if (idx >= total) return;
+  const int c = idx & 3, lane = (idx >> 2) & 31;
+  const size_t rest = idx >> 7;
+  const int kb = (int)(rest % n_kb), rb = (int)(rest / n_kb);
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t w = 0;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int ss = s & 3;
+    const int row = rb * RB + g + 8 * (ss & 1);
+    const int k = kb * KB + 16 * c + 2 * t + 8 * (ss >> 1) + (s >> 2);
+    if (row < N) {
+      const uint8_t b = qw[(size_t)(k >> 1) * N + row];
+      w |= (uint32_t)((b >> ((k & 1) * 4)) & 0xF) << (4 * s);
+    }
+  }
+  out[idx] = w;
+}
+
+__global__ void q4_untile_mma_kernel(const uint32_t* __restrict__ tiled, uint8_t* __restrict__ qw, int N, int K) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one packed byte [j][o]
+  const size_t total = (size_t)(K / 2) * N;
+  if (idx >= total) return;
+  const int o = (int)(idx % N), j = (int)(idx / N);
+  const int n_kb = K / KB;
+  uint8_t b = 0;
+#pragma unroll
+  for (int nr = 0; nr < 2; ++nr) {
+    const int k = 2 * j + nr;
+    const int kb = k / KB, kl = k % KB, c = kl >> 4, k16 = kl & 15;
+    const int hi8 = k16 >> 3, t = (k16 & 7) >> 1, odd = k16 & 1;
+    const int rb = o / RB, rl = o % RB, g = rl & 7, r8 = rl >> 3;
+    const int s = (hi8 << 1 | r8) + 4 * odd;
+    const uint32_t w = tiled[(((size_t)rb * n_kb + kb) * 32 + (g * 4 + t)) * 4 + c];
+    b |= (uint8_t)(((w >> (4 * s)) & 0xF) << (4 * nr));
+  }
+  qw[idx] = b;
+}
+
+}  // namespace q4mv
+}  // namespace b2l
+
+using namespace b2l;
+using namespace b2l::q4mv;
+
+extern "C" size_t b2l_q4_tiled_mma_bytes(int N, int K) {
+  if (N <= 0 || K <= 0 || K % KB != 0) return 0;
+  return (size_t)((N + RB - 1) / RB) * (K / KB) * KB_BYTES;
+}
+
+extern "C" int b2l_q4_tile_mma(const void* qw, void* qw_tiled, int N, int K, b2l_stream_t stream) {
+  B2L_CHECK_ARG(qw && qw_tiled && N > 0 && K > 0, "b2l_q4_tile_mma: bad argument");
+  B2L_CHECK_SUPPORTED(K % KB == 0, "b2l_q4_tile_mma: in_features %d must be a multiple of %d", K, KB);
+  const size_t total = b2l_q4_tiled_mma_bytes(N, K) / 4;
+  q4_tile_mma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)qw, (uint32_t*)qw_tiled, N, K);
+  B2L_LAUNCH_CHECK("q4_tile_mma_kernel");
+  return 0;
+}
+
+extern "C" int b2l_q4_untile_mma(const void* qw_tiled, void* qw, int N, int K, b2l_stream_t stream) {
+  B2L_CHECK_ARG(qw && qw_tiled && N > 0 && K > 0, "b2l_q4_untile_mma: bad argument");
+  B2L_CHECK_SUPPORTED(K % KB == 0, "b2l_q4_untile_mma: in_features %d must be a multiple of %d", K, KB);
+  const size_t total = (size_t)(K / 2) * N;
+  q4_untile_mma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)qw_tiled, (uint8_t*)qw, N, K);
+  B2L_LAUNCH_CHECK("q4_untile_mma_kernel");
+  return 0;
+}
+
+extern "C" int b2l_q4_gemv(const b2l_q4_linear_args* a, b2l_stream_t stream) {
+  B2L_CHECK_ARG(a != nullptr, "b2l_q4_gemv: null args");
+  B2L_CHECK_ARG(a->x && a->qw_tiled && a->scales && a->zeros && a->y, "b2l_q4_gemv: null pointer");
+  B2L_CHECK_SUPPORTED(a->M == 1, "b2l_q4_gemv: M=%d (this kernel is the batch-1 path; use b2l_q4_linear_tc)", a->M);
+  B2L_CHECK_SUPPORTED(a->K > 0 && a->K % KB == 0 && a->K <= 6 * NCW * 32 * 8, "b2l_q4_gemv: K=%d must be a multiple of %d and <= %d", a->K, KB, 6 * NCW * 32 * 8);
+  B2L_CHECK_ARG(a->N > 0, "b2l_q4_gemv: bad N");
+  B2L_CHECK_ARG(((uintptr_t)a->x % 16 == 0) && ((uintptr_t)a->qw_tiled % 16 == 0), "b2l_q4_gemv: x / qw_tiled must be 16-byte aligned");
+  B2L_CHECK_ARG(a->sz_dtype == B2L_BF16 || a->sz_dtype == B2L_F32, "b2l_q4_gemv: bad sz_dtype");
+  if (a->prologue == B2L_PRO_RMSNORM)
+    B2L_CHECK_ARG(a->norm_scale && ((uintptr_t)a->norm_scale % 16 == 0), "b2l_q4_gemv: RMSNorm prologue needs a 16-byte aligned scale");
+  else
+    B2L_CHECK_ARG(a->prologue == B2L_PRO_NONE, "b2l_q4_gemv: bad prologue %d", a->prologue);
+  if (a->epilogue == B2L_EPI_RESIDUAL) B2L_CHECK_ARG(a->res != nullptr, "b2l_q4_gemv: RESIDUAL epilogue needs res");
+  else if (a->epilogue == B2L_EPI_SWIGLU) B2L_CHECK_SUPPORTED(a->N % RB == 0, "b2l_q4_gemv: SWIGLU needs N %% 16 == 0");
+  else B2L_CHECK_ARG(a->epilogue == B2L_EPI_STORE, "b2l_q4_gemv: bad epilogue %d", a->epilogue);
+
+  Params p;
+  p.x = (const __nv_bfloat16*)a->x;
+  p.qwt = (const uint8_t*)a->qw_tiled;
+  p.scales = a->scales; p.zeros = a->zeros; p.szdt = a->sz_dtype;
+  p.y = (__nv_bfloat16*)a->y;
+  p.N = a->N; p.K = a->K;
+  p.n_rb = (a->N + RB - 1) / RB;
+  p.prologue = a->prologue; p.norm_scale = (const __nv_bfloat16*)a->norm_scale; p.eps = a->eps;
+  p.epilogue = a->epilogue; p.res = (const __nv_bfloat16*)a->res;
+  // ring: as deep as fits two CTAs per SM
+  const uint32_t fixed = smem_layout(0, a->K).total;
+  int nst = (int)((110u * 1024u - fixed) / STAGE_BYTES);
+  if (nst > MAX_STAGES) nst = MAX_STAGES;
+  if (nst < 2) nst = 2;
+  p.nst = nst;
+  const SmemLayout L = smem_layout(nst, a->K);
+  static size_t configured_smem = 0;
+  if (L.total > configured_smem) {
+    B2L_CUDA(cudaFuncSetAttribute(q4_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    configured_smem = L.total;
+  }
+  int grid = a->split_k > 0 ? a->split_k : 2 * sm_count();  // split_k doubles as a grid override for tuning
+  if (grid > p.n_rb) grid = p.n_rb;
+  LaunchCfg lc(dim3(grid), dim3(NTHREADS), L.total, (cudaStream_t)stream, (a->flags & B2L_F_PDL) != 0, 1);
+  B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, q4_gemv_kernel, p));
+  return 0;
+}

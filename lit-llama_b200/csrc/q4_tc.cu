@@ -34,12 +34,16 @@ constexpr int G = 2;                     // slabs per stage / per A buffer
 constexpr int STAGE_BYTES = G * SLAB_BYTES;
 constexpr int NAB = 3;                   // A buffers in TMEM
 constexpr int A_COLS = G * 16;           // 32-bit columns per A buffer (K = 64 bf16)
-constexpr int D_COL = NAB * A_COLS;      // accumulator columns start
+constexpr int D_COL = NAB * A_COLS;      // accumulator columns start (96)
 constexpr int TMEM_COLS = 128;
-constexpr int NCONV = 128;               // convert threads (warps 0..3)
-constexpr int NTHREADS = 192;            // + warp 4 (TMA producer, TMEM alloc) + warp 5 (MMA issuer)
+constexpr int NGROUPS = 2;               // convert warp groups, alternating stages
+constexpr int NCONV = 128 * NGROUPS;     // convert threads (warps 0..7)
+constexpr int PRODUCER_WARP = NCONV / 32;      // warp 8: TMA producer, TMEM alloc/dealloc
+constexpr int MMA_WARP = PRODUCER_WARP + 1;    // warp 9: MMA issuer
+constexpr int NTHREADS = NCONV + 64;
 constexpr int MAX_M = 16;
 constexpr int MAX_STAGES = 16;
+constexpr int SMEM_BUDGET = 74 * 1024;   // three CTAs per SM
 
 struct Params {
   const __nv_bfloat16* x; int ldx;
@@ -185,7 +189,7 @@ __host__ __device__ inline SmemLayout smem_layout(int nst_ring, int kseg_max, in
   L.xb = o;   o += (uint32_t)(kseg_max / 8) * kcb;
   L.part = o; o += TILE_N * M * 4;  // [m][row] fp32 partials of this rank (DSMEM-read by rank 0)
   L.xsum = o; o += MAX_M * 4;
-  L.red = o;  o += 4 * MAX_M * 4;  // per-warp partials
+  L.red = o;  o += (NCONV / 32) * MAX_M * 4;  // per-warp partials
   o = (o + 7u) & ~7u;
   L.bars = o; o += (2 * MAX_STAGES + 2 * NAB + 2) * 8;
   L.tmem_slot = o; o += 8;
@@ -193,7 +197,17 @@ __host__ __device__ inline SmemLayout smem_layout(int nst_ring, int kseg_max, in
   return L;
 }
 
-__global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) {
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 3) q4_linear_tc_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const SmemLayout L = smem_layout(p.nst_ring, p.kseg_max, p.kcb, p.M);
   const uint32_t sbase = smem_u32(smem);
@@ -232,126 +246,193 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
     mbar_init(bar_x_ready, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(sbase + L.tmem_slot, TMEM_COLS);
+  __syncthreads();
+
+  // ===================== TMA producer (warp 8, lane 0): stream the packed slabs of this rank ==========
+  // The first ring-full of stages is requested before anything else (TMEM allocation included):
+  // the weights do not depend on the previous kernel, and under PDL this CTA may have to wait
+  // for TMEM while the previous kernel still holds it.
+  const uint8_t* w_src = p.qwt + ((size_t)nt * slabs_total + slab0) * SLAB_BYTES;
+  const int n_first = min(nstages, p.nst_ring);
+  if (warp == PRODUCER_WARP) {
+    if (lane == 0) {
+      for (int st = 0; st < n_first; ++st) {
+        const int ns = min(G, nslab - st * G);
+        const uint32_t bytes = (uint32_t)ns * SLAB_BYTES;
+        mbar_expect_tx(bar_w_full + st * 8, bytes);
+        tma_bulk_g2s(sbase + L.ring + st * STAGE_BYTES, w_src + (size_t)st * STAGE_BYTES, bytes, bar_w_full + st * 8);
+        if (st < 20) B2L_TRACE(108 + st);
+      }
+      pdl_launch_dependents();  // the next kernel's CTAs may start prefetching their weights
+    }
+    __syncwarp();
+  }
+  if (warp == PRODUCER_WARP) tmem_alloc(sbase + L.tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tid == 0) B2L_TRACE(1);
 
-  if (warp == 4) {
-    // ===================== TMA producer: stream the packed slabs of this rank =====================
+  if (warp == PRODUCER_WARP) {
     if (lane == 0) {
-      const uint8_t* src = p.qwt + ((size_t)nt * slabs_total + slab0) * SLAB_BYTES;
-      for (int st = 0; st < nstages; ++st) {
-        const int slot = st % p.nst_ring, it = st / p.nst_ring;
-        mbar_wait(bar_w_empty + slot * 8, (it & 1) ^ 1);
+      int slot = 0;
+      uint32_t phase = 0;  // second use of slot 0 waits for its first release
+      for (int st = n_first; st < nstages; ++st) {
+        mbar_wait(bar_w_empty + slot * 8, phase);
         const int ns = min(G, nslab - st * G);
         const uint32_t bytes = (uint32_t)ns * SLAB_BYTES;
         mbar_expect_tx(bar_w_full + slot * 8, bytes);
-        tma_bulk_g2s(sbase + L.ring + slot * STAGE_BYTES, src + (size_t)st * STAGE_BYTES, bytes, bar_w_full + slot * 8);
+        tma_bulk_g2s(sbase + L.ring + slot * STAGE_BYTES, w_src + (size_t)st * STAGE_BYTES, bytes, bar_w_full + slot * 8);
         if (st < 20) B2L_TRACE(108 + st);
+        if (++slot == p.nst_ring) { slot = 0; phase ^= 1; }
       }
-      // every weight byte of this CTA is now requested: let the next kernel's CTAs start
-      pdl_launch_dependents();
     }
     __syncwarp();
-  } else if (warp == 5) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      mbar_wait(bar_x_ready, 0);
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    mbar_wait(bar_x_ready, 0);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + D_COL;
+    const uint32_t kcb16 = (uint32_t)p.kcb >> 4;
+    // descriptor of the first 8-k column; one K=16 MMA advances it by two columns
+    uint64_t bdesc = make_b_desc(sbase + L.xb, p.kcb, p.kcb == 256 ? 128 : 0);
+    uint32_t accumulate = 0;
+    int ab = 0;
+    uint32_t aphase = 0;
+    for (int st = 0; st < nstages; ++st) {
+      mbar_wait(bar_a_full + ab * 8, aphase);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + D_COL;
-      uint32_t accumulate = 0;
-      for (int st = 0; st < nstages; ++st) {
-        const int ab = st % NAB, it = st / NAB;
-        mbar_wait(bar_a_full + ab * 8, it & 1);
-        tc_fence_after();
-        if (st < 20) B2L_TRACE(64 + st);
-        const int ns = min(G, nslab - st * G);
-        for (int s = 0; s < ns; ++s) {
+      if (st < 20 && lane == 0) B2L_TRACE(64 + st);
+      const int ns = min(G, nslab - st * G);
+      if (elect_one()) {
+        const uint32_t a_tmem = tmem_base + ab * A_COLS;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t a_tmem = tmem_base + ab * A_COLS + s * 16 + h * 8;
-            const int kc = ((st * G + s) * SLAB_K + h * 16) / 8;  // 8-k column index inside the segment
-            const uint64_t bdesc = make_b_desc(sbase + L.xb + kc * p.kcb, p.kcb, p.kcb == 256 ? 128 : 0);
-            tc_mma_ts(d_tmem, a_tmem, bdesc, IDESC, accumulate);
+        for (int j = 0; j < 2 * G; ++j) {
+          if (j < 2 * ns) {
+            tc_mma_ts(d_tmem, a_tmem + j * 8, bdesc + (uint64_t)(2 * j * kcb16), IDESC, accumulate);
             accumulate = 1;
           }
         }
         tc_commit(bar_a_empty + ab * 8);  // arrives when the MMAs above have read A
-        if (st < 20) B2L_TRACE(84 + st);
       }
-      tc_commit(bar_d_full);
+      __syncwarp();
+      accumulate = 1;
+      bdesc += (uint64_t)(4 * G * kcb16);
+      if (st < 20 && lane == 0) B2L_TRACE(84 + st);
+      if (++ab == NAB) { ab = 0; aphase ^= 1; }
     }
+    if (elect_one()) tc_commit(bar_d_full);
     __syncwarp();
-  } else {
-    // ===================== convert warps (thread = output row of the tile) =====================
+  } else if (warp < PRODUCER_WARP) {
+    // ===================== convert warps (thread = output row of the tile; two groups alternate stages) =====
+    const int group = warp >> 2;       // 0 or 1
+    const int row = tid & (TILE_N - 1);
     // -- activations: wait for the producing kernel, normalise, lay out as the B operand
     pdl_wait();
     if (tid == 0) B2L_TRACE(2);
     float* xsum = reinterpret_cast<float*>(smem + L.xsum);
-    float* red = reinterpret_cast<float*>(smem + L.red);
+    float* red = reinterpret_cast<float*>(smem + L.red);  // [8 warps][MAX_M]
     {
-      // zero the B rows that carry no batch row (rows M..15, or M..7 when aliased)
       const int rows = (p.kcb == 256) ? 16 : 8;
       const int nkc = kseg / 8;
-      for (int i = tid; i < nkc * rows; i += NCONV) {
-        const int kc = i / rows, r = i % rows;
-        if (r >= p.M) {
-          uint4* dst = reinterpret_cast<uint4*>(smem + L.xb + kc * p.kcb + (r >> 3) * 128 + (r & 7) * 16);
-          *dst = make_uint4(0, 0, 0, 0);
+      if (p.M < rows) {
+        for (int i = tid; i < nkc * rows; i += NCONV) {
+          const int kc = i / rows, r = i % rows;
+          if (r >= p.M)
+            *reinterpret_cast<uint4*>(smem + L.xb + kc * p.kcb + (r >> 3) * 128 + (r & 7) * 16) = make_uint4(0, 0, 0, 0);
         }
       }
       for (int m = 0; m < p.M; ++m) {
         const __nv_bfloat16* xr = p.x + (size_t)m * p.ldx;
+        const bool norm = (p.prologue == B2L_PRO_RMSNORM);
+        // issue every global load of this row up front (one round trip): the whole row for the
+        // sum of squares (4 chunks of 2048 elements in registers), this rank's segment, and the norm scale
+        constexpr int MAXC = 4;
+        uint4 full[MAXC];
+        if (norm) {
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) {
+            const int k = (c * NCONV + tid) * 8;
+            full[c] = (k < p.K) ? *reinterpret_cast<const uint4*>(xr + k) : make_uint4(0, 0, 0, 0);
+          }
+        }
+        // this rank's K segment: up to XC chunks of 8 elements per thread (kseg <= XC * NCONV * 8, host-checked)
+        constexpr int XC = 2;
+        uint4 u[XC], sc[XC];
+#pragma unroll
+        for (int c = 0; c < XC; ++c) {
+          const int kk = (c * NCONV + tid) * 8;
+          u[c] = make_uint4(0, 0, 0, 0);
+          sc[c] = make_uint4(0, 0, 0, 0);
+          if (kk < kseg) {
+            u[c] = *reinterpret_cast<const uint4*>(xr + k0 + kk);
+            if (norm) sc[c] = *reinterpret_cast<const uint4*>(p.norm_scale + k0 + kk);
+          }
+        }
         float rinv = 1.f;
-        if (p.prologue == B2L_PRO_RMSNORM) {
+        if (norm) {
           float ss = 0.f;
-          for (int k = tid * 8; k < p.K; k += NCONV * 8) {
-            uint4 u = *reinterpret_cast<const uint4*>(xr + k);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          if (p.K > MAXC * NCONV * 8) {  // very wide rows: remaining chunks the slow way
+            for (int k = (MAXC * NCONV + tid) * 8; k < p.K; k += NCONV * 8) {
+              uint4 t = *reinterpret_cast<const uint4*>(xr + k);
+              const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float a = __uint_as_float(w[q] << 16), b = __uint_as_float(w[q] & 0xffff0000u);
+                ss += rbf(a * a) + rbf(b * b);
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) {
+            const uint32_t w[4] = {full[c].x, full[c].y, full[c].z, full[c].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float a = __uint_as_float(w[q] << 16), b = __uint_as_float(w[q] & 0xffff0000u);
-              ss += rbf(a * a);
-              ss += rbf(b * b);
+              ss += rbf(a * a) + rbf(b * b);
             }
           }
           ss = warp_sum(ss);
           if (lane == 0) red[warp * MAX_M + m] = ss;
           named_bar_sync(1, NCONV);
-          ss = red[0 * MAX_M + m] + red[1 * MAX_M + m] + red[2 * MAX_M + m] + red[3 * MAX_M + m];
+          ss = 0.f;
+#pragma unroll
+          for (int w = 0; w < NCONV / 32; ++w) ss += red[w * MAX_M + m];
           rinv = rms_rinv(ss, p.K, p.eps);
           named_bar_sync(1, NCONV);
         }
         float sx = 0.f;
-        for (int kk = tid * 8; kk < kseg; kk += NCONV * 8) {
-          uint4 u = *reinterpret_cast<const uint4*>(xr + k0 + kk);
-          if (p.prologue == B2L_PRO_RMSNORM) {
-            uint4 sc = *reinterpret_cast<const uint4*>(p.norm_scale + k0 + kk);
-            uint32_t w[4] = {u.x, u.y, u.z, u.w};
-            const uint32_t g[4] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float a = rms_apply(__uint_as_float(w[q] << 16), rinv, __uint_as_float(g[q] << 16));
-              float b = rms_apply(__uint_as_float(w[q] & 0xffff0000u), rinv, __uint_as_float(g[q] & 0xffff0000u));
-              sx += a + b;
-              w[q] = (__float_as_uint(a) >> 16) | (__float_as_uint(b) & 0xffff0000u);
+        for (int c = 0; c < XC; ++c) {
+          const int kk = (c * NCONV + tid) * 8;
+          if (kk < kseg) {
+            uint32_t w[4] = {u[c].x, u[c].y, u[c].z, u[c].w};
+            if (norm) {
+              const uint32_t g[4] = {sc[c].x, sc[c].y, sc[c].z, sc[c].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float a = rms_apply(__uint_as_float(w[q] << 16), rinv, __uint_as_float(g[q] << 16));
+                float b = rms_apply(__uint_as_float(w[q] & 0xffff0000u), rinv, __uint_as_float(g[q] & 0xffff0000u));
+                sx += a + b;
+                w[q] = (__float_as_uint(a) >> 16) | (__float_as_uint(b) & 0xffff0000u);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) sx += __uint_as_float(w[q] << 16) + __uint_as_float(w[q] & 0xffff0000u);
             }
-            u = make_uint4(w[0], w[1], w[2], w[3]);
-          } else {
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) sx += __uint_as_float(w[q] << 16) + __uint_as_float(w[q] & 0xffff0000u);
+            *reinterpret_cast<uint4*>(smem + L.xb + (kk / 8) * p.kcb + (m >> 3) * 128 + (m & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
           }
-          uint4* dst = reinterpret_cast<uint4*>(smem + L.xb + (kk / 8) * p.kcb + (m >> 3) * 128 + (m & 7) * 16);
-          *dst = u;
         }
         sx = warp_sum(sx);
         if (lane == 0) red[warp * MAX_M + m] = sx;
         named_bar_sync(1, NCONV);
-        if (tid == 0) xsum[m] = red[0 * MAX_M + m] + red[1 * MAX_M + m] + red[2 * MAX_M + m] + red[3 * MAX_M + m];
+        if (tid == 0) {
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < NCONV / 32; ++w) t += red[w * MAX_M + m];
+          xsum[m] = t;
+        }
       }
       fence_proxy_async_smem();  // B operand written with generic stores, read by the tensor core
       named_bar_sync(1, NCONV);
@@ -359,19 +440,21 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
       if (tid == 0) B2L_TRACE(3);
     }
 
-    // -- weights: smem slab -> registers -> TMEM A operand
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    for (int st = 0; st < nstages; ++st) {
-      const int slot = st % p.nst_ring, rit = st / p.nst_ring;
-      const int ab = st % NAB, ait = st / NAB;
+    // -- weights: smem slab -> registers -> TMEM A operand.  Group g takes stages g, g+2, ...
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    int slot = group % p.nst_ring;
+    uint32_t rphase = (group >= p.nst_ring) ? 1u : 0u;
+    int ab = group;                   // NAB == 3: (st % 3) advances by 2 each step
+    uint32_t aphase = 1;              // parity to wait on for "A buffer free"; flips when ab wraps
+    for (int st = group; st < nstages; st += NGROUPS) {
       const int ns = min(G, nslab - st * G);
-      mbar_wait(bar_w_full + slot * 8, rit & 1);
+      mbar_wait(bar_w_full + slot * 8, rphase);
       if (tid == 0 && st < 20) B2L_TRACE(4 + st);
       uint4 wv[G];
 #pragma unroll
       for (int s = 0; s < G; ++s)
-        if (s < ns) wv[s] = *reinterpret_cast<const uint4*>(smem + L.ring + slot * STAGE_BYTES + s * SLAB_BYTES + tid * 16);
-      mbar_wait(bar_a_empty + ab * 8, (ait & 1) ^ 1);
+        if (s < ns) wv[s] = *reinterpret_cast<const uint4*>(smem + L.ring + slot * STAGE_BYTES + s * SLAB_BYTES + row * 16);
+      mbar_wait(bar_a_empty + ab * 8, aphase);
       tc_fence_after();
       if (tid == 0 && st < 20) B2L_TRACE(24 + st);
 #pragma unroll
@@ -393,24 +476,30 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
         mbar_arrive(bar_a_full + ab * 8);
       }
       if (tid == 0 && st < 20) B2L_TRACE(44 + st);
+      slot += NGROUPS;
+      while (slot >= p.nst_ring) { slot -= p.nst_ring; rphase ^= 1; }
+      ab += NGROUPS;
+      if (ab >= NAB) { ab -= NAB; aphase ^= 1; }
     }
 
-    // -- epilogue part 1: accumulator -> scaled partial of this rank
-    mbar_wait(bar_d_full, 0);
-    tc_fence_after();
-    if (tid == 0) B2L_TRACE(104);
-    uint32_t acc[16];
-    tmem_ld16(tmem_base + lane_base + D_COL, acc);
-    const int o = min(nt * TILE_N + tid, p.N - 1);  // padded rows of the last tile are never stored
-    const float sc = load_sz(p.scales, p.szdt, o);
-    const float zz = 128.0f + load_sz(p.zeros, p.szdt, o);
-    float* part = reinterpret_cast<float*>(smem + L.part);
+    // -- epilogue part 1 (group 0): accumulator -> scaled partial of this rank
+    if (group == 0) {
+      mbar_wait(bar_d_full, 0);
+      tc_fence_after();
+      if (tid == 0) B2L_TRACE(104);
+      uint32_t acc[16];
+      tmem_ld16(tmem_base + lane_base + D_COL, acc);
+      const int o = min(nt * TILE_N + row, p.N - 1);  // padded rows of the last tile are never stored
+      const float sc = load_sz(p.scales, p.szdt, o);
+      const float zz = 128.0f + load_sz(p.zeros, p.szdt, o);
+      float* part = reinterpret_cast<float*>(smem + L.part);
 #pragma unroll
-    for (int m = 0; m < MAX_M; ++m)
-      if (m < p.M) part[m * TILE_N + tid] = sc * (__uint_as_float(acc[m]) - zz * xsum[m]);
+      for (int m = 0; m < MAX_M; ++m)
+        if (m < p.M) part[m * TILE_N + row] = sc * (__uint_as_float(acc[m]) - zz * xsum[m]);
+    }
   }
 
-  // ===================== cross-rank reduction + epilogue (rank 0) =====================
+  // ===================== cross-rank reduction + epilogue (rank 0, group 0) =====================
   tc_fence_before();
   if (S > 1) cluster_sync_all(); else __syncthreads();
   if (tid == 0) B2L_TRACE(105);
@@ -433,7 +522,7 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
 #pragma unroll
       for (int m = 0; m < MAX_M; ++m)
         if (m < p.M) fin[m * TILE_N + tid] = rbf(tot[m]);
-      named_bar_sync(1, NCONV);
+      named_bar_sync(2, 128);
       if (tid < 64) {
         const int oo = nt * 64 + tid;
 #pragma unroll
@@ -458,7 +547,7 @@ __global__ void __launch_bounds__(NTHREADS) q4_linear_tc_kernel(const Params p) 
   }
   if (tid == 0) B2L_TRACE(106);
   if (S > 1) cluster_sync_all(); else __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == PRODUCER_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
   if (tid == 0) B2L_TRACE(107);
 }
 
@@ -535,12 +624,21 @@ extern "C" int b2l_q4_untile(const void* qw_tiled, void* qw, int N, int K, b2l_s
 }
 
 namespace b2l {
+// Split-K (cluster size) choice: one wave of at most 3 CTAs per SM if possible; cost model =
+// waves x (slabs per CTA + a fixed per-CTA cost worth ~24 slabs of prologue/epilogue latency).
 int q4_pick_split(int n_tiles, int slabs_total) {
-  // enough CTAs to cover the machine about twice, B operand of one rank <= 1024 k when possible
-  int S = 1;
-  while (S < 8 && (n_tiles * S < 2 * sm_count() || slabs_total / S > 32)) S *= 2;
-  while (S > 1 && slabs_total / S < 4) S /= 2;
-  return S;
+  const int slots = 3 * sm_count();
+  int best = 1;
+  long best_cost = -1;
+  for (int S = 1; S <= 8; ++S) {
+    if (slabs_total / S < 2) break;
+    const int per = (slabs_total + S - 1) / S;
+    if (per * q4tc::SLAB_K > 2 * q4tc::NCONV * 8) continue;  // two activation chunks per convert thread
+    const long waves = ((long)n_tiles * S + slots - 1) / slots;
+    const long cost = waves * (per + 24);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = S; }
+  }
+  return best_cost < 0 ? 8 : best;
 }
 }  // namespace b2l
 
@@ -564,8 +662,8 @@ extern "C" int b2l_q4_linear_tc(const b2l_q4_linear_args* a, b2l_stream_t stream
   const int n_tiles = (a->N + TILE_N - 1) / TILE_N;
   const int slabs_total = a->K / SLAB_K;
   int S = a->split_k > 0 ? a->split_k : q4_pick_split(n_tiles, slabs_total);
-  B2L_CHECK_SUPPORTED(S == 1 || S == 2 || S == 4 || S == 8, "b2l_q4_linear_tc: split_k=%d must be 1, 2, 4 or 8", S);
-  while (S > 1 && slabs_total < S) S /= 2;
+  B2L_CHECK_SUPPORTED(S >= 1 && S <= 8, "b2l_q4_linear_tc: split_k=%d must be in 1..8", S);
+  while (S > 1 && slabs_total < 2 * S) --S;
 
   Params p;
   p.x = (const __nv_bfloat16*)a->x; p.ldx = a->ldx;
@@ -579,9 +677,16 @@ extern "C" int b2l_q4_linear_tc(const b2l_q4_linear_args* a, b2l_stream_t stream
   p.trace = (unsigned long long*)a->trace;
   const int max_slabs = (slabs_total + S - 1) / S;
   p.kseg_max = max_slabs * SLAB_K;
-  p.kcb = ((a->flags & B2L_F_ALIAS_N) && a->M <= 8) ? 128 : 256;
+  p.kcb = (!(a->flags & B2L_F_NO_ALIAS_N) && a->M <= 8) ? 128 : 256;  // rows 8..15 of B alias rows 0..7
+  B2L_CHECK_SUPPORTED(p.kseg_max <= 2 * NCONV * 8, "b2l_q4_linear_tc: K/split_k = %d > %d: raise split_k (K=%d, split_k=%d)",
+                      p.kseg_max, 2 * NCONV * 8, a->K, S);
   const int stages_needed = (max_slabs + G - 1) / G;
-  p.nst_ring = stages_needed < MAX_STAGES ? stages_needed : MAX_STAGES;
+  // ring depth: the whole K range in flight when it fits the per-CTA budget (3 CTAs per SM), >= 4 stages
+  const uint32_t fixed = smem_layout(0, p.kseg_max, p.kcb, p.M).total;
+  int ring = fixed < (uint32_t)SMEM_BUDGET ? (int)((SMEM_BUDGET - fixed) / STAGE_BYTES) : 0;
+  if (ring < 4) ring = 4;
+  if (ring > MAX_STAGES) ring = MAX_STAGES;
+  p.nst_ring = stages_needed < ring ? stages_needed : ring;
   if (p.nst_ring < 1) p.nst_ring = 1;
   const SmemLayout L = smem_layout(p.nst_ring, p.kseg_max, p.kcb, p.M);
   B2L_CHECK_SUPPORTED(L.total <= 200 * 1024, "b2l_q4_linear_tc: shared memory %u B too large (K=%d, split_k=%d)", L.total, a->K, S);

@@ -159,7 +159,7 @@ class CausalSelfAttention(nn.Module):
                 self._ring = torch.zeros(1, dtype=torch.int32, device=x.device)
             if not self._ring_shared:  # stand-alone use: this module owns the roll state (model.py:214-218)
                 L.check(lib.b2l_ring_advance(pos.data_ptr(), T, self._ring.data_ptr(), S, L.stream_ptr()), "b2l_ring_advance")
-            work = torch.empty(lib.b2l_attn_workspace_bytes(B, self.n_head, hs, T, S) // 4 + 1, device=x.device, dtype=torch.float32)
+            work = torch.zeros(lib.b2l_attn_workspace_bytes(B, self.n_head, hs, T, S) // 4 + 1, device=x.device, dtype=torch.float32)
             flags = 0 if _rope_is_table else 4  # B2L_F_ROPE_ROWS
             rc = lib.b2l_attention(qkv.data_ptr(), cache_k.data_ptr(), cache_v.data_ptr(), rope32.data_ptr(), pos.data_ptr(),
                                    self._ring.data_ptr(), y.data_ptr(), work.data_ptr(), B, T, self.n_head, hs, S,
@@ -243,12 +243,15 @@ class _DecodeState:
         self.hid = torch.empty((B, n_hidden), **bf)
         self.logits = torch.empty((B, 1, cfg.padded_vocab_size), **bf)
         lib = L.lib()
-        self.work = torch.empty(lib.b2l_attn_workspace_bytes(B, nh, hs, 1, S) // 4 + 1, device=device, dtype=torch.float32)
+        self.work = torch.zeros(lib.b2l_attn_workspace_bytes(B, nh, hs, 1, S) // 4 + 1, device=device, dtype=torch.float32)
         self.keep = []  # tensors the argument block points into
 
+        gemv = (B == 1)  # batch 1: mma.sync kernel and its tiling; batch 2..16: tcgen05 kernel and its tiling
+
         def q4(lin: ColBlockQuantizedLinear) -> L.Q4Weight:
-            t = lin.tiled()
-            return L.Q4Weight(t.data_ptr(), lin.scales.data_ptr(), lin.zeros.data_ptr(), lin.out_features, lin.in_features)
+            t = lin.tiled_mma() if gemv else lin.tiled()
+            return L.Q4Weight(None if gemv else t.data_ptr(), t.data_ptr() if gemv else None, lin.scales.data_ptr(),
+                              lin.zeros.data_ptr(), lin.out_features, lin.in_features)
 
         def bf16(p: torch.Tensor) -> torch.Tensor:
             t = p.detach()
@@ -259,12 +262,13 @@ class _DecodeState:
 
         layers = (L.Layer * cfg.n_layer)()
         for i, blk in enumerate(model.transformer.h):
-            fc12 = model._fc12(i)
+            fc12 = model._fc12(i, gemv)
             k, v = model.kv_caches[i]
             layers[i] = L.Layer(
                 rms_1=bf16(blk.rms_1.scale).data_ptr(), rms_2=bf16(blk.rms_2.scale).data_ptr(),
                 c_attn=q4(blk.attn.c_attn), c_proj=q4(blk.attn.c_proj),
-                c_fc12=L.Q4Weight(fc12[0].data_ptr(), fc12[1].data_ptr(), fc12[2].data_ptr(), 2 * n_hidden, C_),
+                c_fc12=L.Q4Weight(None if gemv else fc12[0].data_ptr(), fc12[0].data_ptr() if gemv else None,
+                                  fc12[1].data_ptr(), fc12[2].data_ptr(), 2 * n_hidden, C_),
                 mlp_proj=q4(blk.mlp.c_proj), k_cache=k.data_ptr(), v_cache=v.data_ptr())
         self.layers = layers
         lin0 = model.lm_head
@@ -347,36 +351,42 @@ class LLaMA(nn.Module):
             self._ring.zero_()
 
     # ------------------------------------------------------------------ helpers
-    def _fc12(self, i: int):
-        """c_fc1 and c_fc2 of layer i interleaved 64 rows / 64 rows per 128-row tile and
-        re-tiled, so one tcgen05 tile holds silu's argument and its multiplier."""
+    def _fc12(self, i: int, gemv: bool):
+        """c_fc1 and c_fc2 of layer i interleaved (8 rows / 8 rows per 16-row block for the
+        batch-1 kernel, 64 / 64 per 128-row tile for the tcgen05 kernel) and re-tiled, so one
+        tile holds silu's argument and its multiplier and SwiGLU runs in the epilogue."""
         mlp = self.transformer.h[i].mlp
-        key = (mlp.c_fc1.quant_weight.data_ptr(), mlp.c_fc1.quant_weight._version,
+        key = (gemv, mlp.c_fc1.quant_weight.data_ptr(), mlp.c_fc1.quant_weight._version,
                mlp.c_fc2.quant_weight.data_ptr(), mlp.c_fc2.quant_weight._version)
-        hit = self._fc12_cache.get(i)
+        hit = self._fc12_cache.get((i, gemv))
         if hit is not None and hit[0] == key:
             return hit[1]
         nh, K = mlp.c_fc1.out_features, mlp.c_fc1.in_features
-        assert nh % 64 == 0
+        g = 8 if gemv else 64
+        assert nh % g == 0
 
-        def inter(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:  # rows (dim 0) of a, b -> [t][64 a | 64 b]
-            return torch.stack((a.reshape(nh // 64, 64, *a.shape[1:]), b.reshape(nh // 64, 64, *b.shape[1:])), dim=1).reshape(2 * nh, *a.shape[1:])
+        def inter(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:  # rows (dim 0) of a, b -> [t][g of a | g of b]
+            return torch.stack((a.reshape(nh // g, g, *a.shape[1:]), b.reshape(nh // g, g, *b.shape[1:])), dim=1).reshape(2 * nh, *a.shape[1:])
 
         qw = inter(mlp.c_fc1.quant_weight, mlp.c_fc2.quant_weight).t().contiguous().t()  # reference layout (1, 2nh)
         scales = inter(mlp.c_fc1.scales, mlp.c_fc2.scales).contiguous()
         zeros = inter(mlp.c_fc1.zeros, mlp.c_fc2.zeros).contiguous()
         lib = L.lib()
-        tiled = torch.empty(lib.b2l_q4_tiled_bytes(2 * nh, K), dtype=torch.uint8, device=qw.device)
-        L.check(lib.b2l_q4_tile(qw.data_ptr(), tiled.data_ptr(), 2 * nh, K, L.stream_ptr()), "b2l_q4_tile")
+        if gemv:
+            tiled = torch.empty(lib.b2l_q4_tiled_mma_bytes(2 * nh, K), dtype=torch.uint8, device=qw.device)
+            L.check(lib.b2l_q4_tile_mma(qw.data_ptr(), tiled.data_ptr(), 2 * nh, K, L.stream_ptr()), "b2l_q4_tile_mma")
+        else:
+            tiled = torch.empty(lib.b2l_q4_tiled_bytes(2 * nh, K), dtype=torch.uint8, device=qw.device)
+            L.check(lib.b2l_q4_tile(qw.data_ptr(), tiled.data_ptr(), 2 * nh, K, L.stream_ptr()), "b2l_q4_tile")
         val = (tiled, scales, zeros)
-        self._fc12_cache[i] = (key, val)
+        self._fc12_cache[(i, gemv)] = (key, val)
         return val
 
     def _fast_decode_ok(self) -> bool:
         from .quantization import ColBlockQuantizedLinear
 
         def ok(m):
-            return isinstance(m, ColBlockQuantizedLinear) and m.tc_capable
+            return isinstance(m, ColBlockQuantizedLinear) and m.tc_capable and m.gemv_capable
 
         if not ok(self.lm_head) or self.config.n_embd % 8 != 0:
             return False

@@ -44,8 +44,10 @@ class ColBlockQuantizedLinear(torch.nn.Module):
             self.register_buffer("bias", torch.empty((self.out_features,)))
         else:
             self.register_buffer("bias", None)
-        self._tiled = None        # load-time re-tiling for the tcgen05 kernel (not part of state_dict)
+        self._tiled = None        # load-time re-tilings for the kernels (not part of state_dict)
         self._tiled_key = None
+        self._tiled_mma = None
+        self._tiled_mma_key = None
 
     # ------------------------------------------------------------------ packing (load-time, any device)
     def pack_weight(self, weight):
@@ -103,6 +105,23 @@ class ColBlockQuantizedLinear(torch.nn.Module):
             self._tiled, self._tiled_key = t, key
         return self._tiled
 
+    def tiled_mma(self) -> torch.Tensor:
+        """The [N/16][K/64][32 lanes][16 B] re-tiling of the batch-1 kernel (b2l_q4_tile_mma)."""
+        qw = self.quant_weight
+        key = (qw.data_ptr(), qw._version)
+        if self._tiled_mma is None or self._tiled_mma_key != key:
+            self._check_layout()
+            nbytes = L.lib().b2l_q4_tiled_mma_bytes(self.out_features, self.in_features)
+            t = torch.empty(nbytes, dtype=torch.uint8, device=qw.device)
+            L.check(L.lib().b2l_q4_tile_mma(qw.data_ptr(), t.data_ptr(), self.out_features, self.in_features, L.stream_ptr()),
+                    "b2l_q4_tile_mma")
+            self._tiled_mma, self._tiled_mma_key = t, key
+        return self._tiled_mma
+
+    @property
+    def gemv_capable(self) -> bool:
+        return self.tc_capable and self.in_features % 64 == 0 and self.in_features <= 12288
+
     def forward(self, inp):
         L.require_cuda_bf16(inp, "ColBlockQuantizedLinear.forward")
         if self.quant_weight.device != inp.device:
@@ -117,7 +136,13 @@ class ColBlockQuantizedLinear(torch.nn.Module):
         if M == 0:
             return y.reshape(*shape[:-1], N)
         aligned = x.data_ptr() % 16 == 0 and x.stride(0) % 8 == 0
-        if self.tc_capable and aligned and M <= 64:
+        if self.gemv_capable and aligned and M == 1:
+            a = L.Q4LinearArgs(
+                x=x.data_ptr(), ldx=x.stride(0), qw_tiled=self.tiled_mma().data_ptr(), scales=self.scales.data_ptr(),
+                zeros=self.zeros.data_ptr(), sz_dtype=L.sz_dtype_of(self.scales), y=y.data_ptr(), ldy=N, M=1, N=N, K=K,
+                prologue=L.PRO_NONE, norm_scale=None, eps=0.0, epilogue=L.EPI_STORE, res=None, ldres=0, split_k=0, flags=0)
+            L.check(L.lib().b2l_q4_gemv(C.byref(a), L.stream_ptr()), "b2l_q4_gemv")
+        elif self.tc_capable and aligned and M <= 64:
             qt = self.tiled()
             for m0 in range(0, M, 16):
                 mm = min(16, M - m0)

@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "ops", "model", "trace", "bench_layers", "bench_step"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "trace", "bench_layers", "bench_gemv", "bench_step"]
 
 
 def rand_q4(N, K, dev, seed=0, sz_dtype=None, groups=1, bits=4):
@@ -76,6 +76,115 @@ def tile(L, qw, N, K):
     qt = torch.empty(L.lib().b2l_q4_tiled_bytes(N, K), dtype=torch.uint8, device=qw.device)
     L.check(L.lib().b2l_q4_tile(qw.data_ptr(), qt.data_ptr(), N, K, L.stream_ptr()), "tile")
     return qt
+
+
+def tile_mma(L, qw, N, K):
+    import torch
+
+    qt = torch.empty(L.lib().b2l_q4_tiled_mma_bytes(N, K), dtype=torch.uint8, device=qw.device)
+    L.check(L.lib().b2l_q4_tile_mma(qw.data_ptr(), qt.data_ptr(), N, K, L.stream_ptr()), "tile_mma")
+    return qt
+
+
+def gemv_call(L, x, qt, scales, zeros, N, K, *, y=None, prologue=0, norm_scale=None, eps=1e-5, epilogue=0, res=None, grid=0,
+              flags=0, n_out=None):
+    import torch
+
+    n_out = n_out or N
+    if y is None:
+        y = torch.zeros((1, n_out), device=x.device, dtype=torch.bfloat16)
+    a = L.Q4LinearArgs(x=x.data_ptr(), ldx=K, qw_tiled=qt.data_ptr(), scales=scales.data_ptr(), zeros=zeros.data_ptr(),
+                       sz_dtype=L.sz_dtype_of(scales), y=y.data_ptr(), ldy=n_out, M=1, N=N, K=K, prologue=prologue,
+                       norm_scale=None if norm_scale is None else norm_scale.data_ptr(), eps=eps, epilogue=epilogue,
+                       res=None if res is None else res.data_ptr(), ldres=N, split_k=grid, flags=flags)
+    rc = L.lib().b2l_q4_gemv(C.byref(a), L.stream_ptr())
+    if rc != 0:
+        return None, f"rc={rc}: {L.lib().b2l_last_error().decode()}"
+    return y, None
+
+
+def sec_gemv():
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    for (N, K, grid) in [(16, 64, 0), (16, 128, 0), (32, 2048, 0), (48, 4096, 0), (130, 256, 0), (4096, 4096, 0), (4096, 4096, 7),
+                         (12288, 4096, 0), (4096, 11008, 0), (32000, 4096, 0), (22016, 4096, 0), (128, 6400, 0)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=N + K)
+        qt = tile_mma(L, qw, N, K)
+        back = torch.empty_like(qw)
+        L.check(L.lib().b2l_q4_untile_mma(qt.data_ptr(), back.data_ptr(), N, K, L.stream_ptr()), "untile_mma")
+        x = torch.randn(1, K, device=dev).bfloat16()
+        y, err = gemv_call(L, x, qt, sc, z, N, K, grid=grid)
+        torch.cuda.synchronize()
+        if err:
+            print(f"gemv N={N} K={K} grid={grid}: {err}")
+            continue
+        want = ref_linear(x, lv, sc, z)
+        wb = want.float().bfloat16()
+        print(f"gemv N={N} K={K} grid={grid}: roundtrip={bool(torch.equal(back, qw))} relerr={relerr(y, want):.3e} "
+              f"exact_bf16_frac={float((y == wb).float().mean()):.4f}")
+        if N == 16 and K == 64:
+            print("   got ", [round(float(v), 4) for v in y[0, :8]])
+            print("   want", [round(float(v), 4) for v in want[0, :8]])
+    N, K = 512, 1024
+    lv, qw, sc, z = rand_q4(N, K, dev, seed=5)
+    qt = tile_mma(L, qw, N, K)
+    x = (torch.randn(1, K, device=dev) * 0.7).bfloat16()
+    g = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
+    ms = torch.mean(x * x, dim=-1, keepdim=True)
+    xn = g * (x * torch.rsqrt(ms + 1e-5))
+    y, err = gemv_call(L, x, qt, sc, z, N, K, prologue=1, norm_scale=g)
+    torch.cuda.synchronize()
+    print("gemv rmsnorm prologue:", err or f"relerr={relerr(y, ref_linear(xn, lv, sc, z)):.3e}")
+    res = torch.randn(1, N, device=dev).bfloat16()
+    y, err = gemv_call(L, x, qt, sc, z, N, K, epilogue=1, res=res)
+    torch.cuda.synchronize()
+    want = (ref_linear(x, lv, sc, z).float().bfloat16() + res)
+    print("gemv residual:", err or f"relerr={relerr(y, want):.3e} exact={float((y == want).float().mean()):.4f}")
+    buf = res.clone()
+    y, err = gemv_call(L, x, qt, sc, z, N, K, epilogue=1, res=buf, y=buf)
+    torch.cuda.synchronize()
+    print("gemv in-place residual:", err or f"relerr={relerr(buf, want):.3e}")
+    full = ref_linear(x, lv, sc, z).float().bfloat16().reshape(1, N // 16, 2, 8)
+    a, b = full[:, :, 0].reshape(1, -1), full[:, :, 1].reshape(1, -1)
+    want = torch.nn.functional.silu(a) * b
+    y, err = gemv_call(L, x, qt, sc, z, N, K, epilogue=2, n_out=N // 2)
+    torch.cuda.synchronize()
+    print("gemv swiglu:", err or f"relerr={relerr(y, want):.3e} exact={float((y == want).float().mean()):.4f}")
+    y, err = gemv_call(L, x, qt, sc, z, N, K, flags=1)
+    torch.cuda.synchronize()
+    print("gemv pdl flag:", err or f"relerr={relerr(y, ref_linear(x, lv, sc, z)):.3e}")
+
+
+def sec_bench_gemv():
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    lib = L.lib()
+    for (name, N, K) in [("c_attn", 12288, 4096), ("c_proj", 4096, 4096), ("fc12", 22016, 4096), ("mlp_proj", 4096, 11008), ("lm_head", 32000, 4096)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=3)
+        n_copies = max(4, int(400e6 // (N * K // 2)) + 1)
+        qts = [tile_mma(L, qw, N, K) for _ in range(n_copies)]
+        x = torch.randn(1, K, device=dev).bfloat16()
+        y = torch.zeros(1, N, device=dev, dtype=torch.bfloat16)
+        for grid in (0, 148, 444):
+            for flags in (0, 1):
+                args = [L.Q4LinearArgs(x=x.data_ptr(), ldx=K, qw_tiled=qt.data_ptr(), scales=sc.data_ptr(), zeros=z.data_ptr(),
+                                       sz_dtype=0, y=y.data_ptr(), ldy=N, M=1, N=N, K=K, prologue=0, norm_scale=None, eps=1e-5,
+                                       epilogue=0, res=None, ldres=N, split_k=grid, flags=flags) for qt in qts]
+                if lib.b2l_q4_gemv(C.byref(args[0]), L.stream_ptr()) != 0:
+                    print(f"{name} grid={grid}: {lib.b2l_last_error().decode()[:90]}")
+                    continue
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for a in args:
+                        lib.b2l_q4_gemv(C.byref(a), L.stream_ptr())
+                us = _time(g.replay, iters=10, warm=2) / n_copies
+                print(f"gemv {name} N={N} K={K} grid={grid or 296} pdl={flags}: {us:.2f} us/launch  {(N * K / 2) / us / 1e3:.0f} GB/s")
+        del qts
 
 
 def sec_generic():
@@ -350,6 +459,24 @@ def make_args(L, x, qt, scales, zeros, N, K, y, *, prologue=0, norm_scale=None, 
                           split_k=split_k, flags=flags, trace=None if trace is None else trace.data_ptr())
 
 
+def sec_mma_rate():
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    out = torch.zeros(64 * 3, dtype=torch.int64, device=dev)
+    for a_smem in (0, 1):
+        for n_acc in (1, 4):
+            for n_mma in (1, 4, 16):
+                out.zero_()
+                L.check(L.lib().b2l_debug_mma_rate(out.data_ptr(), n_mma, n_acc, a_smem, 8, L.stream_ptr()), "mma_rate")
+                torch.cuda.synchronize()
+                o = out.cpu().reshape(-1, 3)[:8]
+                r = o[3:].float().mean(0)  # skip cold rounds
+                print(f"A_from_{'smem' if a_smem else 'tmem'} n_acc={n_acc} n_mma={n_mma:3d}: issue={r[0]:.0f} cyc ({r[0] / n_mma:.1f}/mma) "
+                      f"commit_issue={r[1]:.0f} total_until_arrive={r[2]:.0f} ({r[2] / n_mma:.1f}/mma)")
+
+
 def sec_trace():
     """clock64 stamps of CTA 0 of one launch: where does a CTA spend its time?"""
     import torch
@@ -399,11 +526,11 @@ def sec_bench_layers():
         qts = [tile(L, qw, N, K) for _ in range(n_copies)]
         x = torch.randn(1, K, device=dev).bfloat16()
         y = torch.zeros(1, N, device=dev, dtype=torch.bfloat16)
-        for S in (2, 4, 8):
-            for flags in (0, 1, 3):
+        for S in (0, 1, 2, 3, 4, 6, 8):
+            for flags in (0,):
                 args = [make_args(L, x, qt, sc, z, N, K, y, split_k=S, flags=flags) for qt in qts]
                 if lib.b2l_q4_linear_tc(C.byref(args[0]), L.stream_ptr()) != 0:
-                    print(f"{name} S={S} flags={flags}: {lib.b2l_last_error().decode()}")
+                    print(f"{name} S={S} flags={flags}: {lib.b2l_last_error().decode()[:90]}")
                     continue
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
