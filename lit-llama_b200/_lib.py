@@ -50,7 +50,7 @@ class DecodeArgs(C.Structure):
         ("idx", c_void_p), ("idx_is_i64", c_int),
         ("input_pos", c_void_p), ("ring_start", c_void_p), ("block_size", c_int),
         ("x", c_void_p), ("qkv", c_void_p), ("att", c_void_p), ("hid", c_void_p), ("attn_work", c_void_p),
-        ("logits", c_void_p), ("flags", c_int),
+        ("logits", c_void_p), ("flags", c_int), ("timeline", c_void_p),
     ]
 
 

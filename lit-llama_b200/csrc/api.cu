@@ -5,6 +5,8 @@
 
 namespace b2l {
 
+extern void* g_attn_timeline;
+
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -60,7 +62,7 @@ extern "C" int b2l_device_info(int* sm, int* cc_major, int* cc_minor) {
 // ---------------------------------------------------------------------------------
 static int q4_call(const b2l_q4_weight& w, const void* x, int ldx, void* y, int ldy, int M, int sz_dtype, int prologue,
                    const void* norm_scale, float eps, int epilogue, const void* res, int ldres, int flags,
-                   b2l_stream_t stream) {
+                   b2l_stream_t stream, void* trace = nullptr) {
   b2l_q4_linear_args a{};
   a.x = x; a.ldx = ldx;
   const bool gemv = (M == 1 && w.qw_mma != nullptr);
@@ -71,6 +73,7 @@ static int q4_call(const b2l_q4_weight& w, const void* x, int ldx, void* y, int 
   a.epilogue = epilogue; a.res = res; a.ldres = ldres;
   a.split_k = 0;
   a.flags = flags;
+  a.trace = gemv ? trace : nullptr;
   if (gemv) return b2l_q4_gemv(&a, stream);
   if (a.qw_tiled == nullptr) {
     set_error("b2l_decode_step: weight has no tiling for batch %d", M);
@@ -96,26 +99,35 @@ extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {
   const int C = d->n_embd, hs = C / d->n_head, B = d->B;
   const int fl = d->flags;
   int rc;
+  // debug timeline: launch i of the step writes uint64[8] at timeline + 64*i (order: per Block c_attn,
+  // attention, c_proj, fc12, mlp_proj; then lm_head)
+  char* tlb = (char*)d->timeline;
+  int li = 0;
+  auto tl = [&]() -> void* { void* r = tlb ? (void*)(tlb + 64 * li) : nullptr; ++li; return r; };
   if ((rc = b2l_ring_advance(d->input_pos, 1, d->ring_start, d->S, stream))) return rc;
   if ((rc = b2l_embedding(d->idx, d->idx_is_i64, d->wte, d->x, B, C, d->vocab, stream))) return rc;
   for (int l = 0; l < d->n_layer; ++l) {
     const b2l_layer& L = d->layers[l];
     if ((rc = q4_call(L.c_attn, d->x, C, d->qkv, 3 * C, B, d->sz_dtype, B2L_PRO_RMSNORM, L.rms_1, d->eps, B2L_EPI_STORE,
-                      nullptr, 0, fl, stream)))
+                      nullptr, 0, fl, stream, tl())))
       return rc;
+    g_attn_timeline = tl();
     if ((rc = b2l_attention(d->qkv, L.k_cache, L.v_cache, d->rope, d->input_pos, d->ring_start, d->att, d->attn_work, B,
-                            1, d->n_head, hs, d->S, d->block_size, fl, stream)))
+                            1, d->n_head, hs, d->S, d->block_size, fl, stream))) {
+      g_attn_timeline = nullptr;
       return rc;
+    }
+    g_attn_timeline = nullptr;
     if ((rc = q4_call(L.c_proj, d->att, C, d->x, C, B, d->sz_dtype, B2L_PRO_NONE, nullptr, 0.f, B2L_EPI_RESIDUAL, d->x, C,
-                      fl, stream)))
+                      fl, stream, tl())))
       return rc;
     if ((rc = q4_call(L.c_fc12, d->x, C, d->hid, d->n_hidden, B, d->sz_dtype, B2L_PRO_RMSNORM, L.rms_2, d->eps,
-                      B2L_EPI_SWIGLU, nullptr, 0, fl, stream)))
+                      B2L_EPI_SWIGLU, nullptr, 0, fl, stream, tl())))
       return rc;
     if ((rc = q4_call(L.mlp_proj, d->hid, d->n_hidden, d->x, C, B, d->sz_dtype, B2L_PRO_NONE, nullptr, 0.f,
-                      B2L_EPI_RESIDUAL, d->x, C, fl, stream)))
+                      B2L_EPI_RESIDUAL, d->x, C, fl, stream, tl())))
       return rc;
   }
   return q4_call(d->lm_head, d->x, C, d->logits, d->vocab, B, d->sz_dtype, B2L_PRO_RMSNORM, d->ln_f, d->eps,
-                 B2L_EPI_STORE, nullptr, 0, fl, stream);
+                 B2L_EPI_STORE, nullptr, 0, fl, stream, tl());
 }

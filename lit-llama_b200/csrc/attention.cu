@@ -208,7 +208,7 @@ __global__ void kv_unroll_kernel(const __nv_bfloat16* __restrict__ cache, const 
 // waits for the c_attn kernel (old cache rows do not depend on the current token).
 // ----------------------------------------------------------------------------------
 constexpr int FD_CHUNK = 128;   // keys per CTA
-constexpr int FD_WARPS = 4;
+constexpr int FD_WARPS = 8;
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -224,35 +224,38 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
                              __nv_bfloat16* __restrict__ v_cache, const float* __restrict__ rope,
                              const int64_t* __restrict__ input_pos, const int32_t* __restrict__ ring_start,
                              __nv_bfloat16* __restrict__ y, float* __restrict__ work, int* __restrict__ tickets,
-                             int n_head, int S, int block_size, int n_split) {
+                             int n_head, int S, int block_size, int n_split, unsigned long long* tl) {
   constexpr int HS = 128;
+  if (threadIdx.x == 0) tl_min(tl, 0);
   const int bh = blockIdx.x, b = bh / n_head, h = bh % n_head, sp = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = n_head * HS;
   const size_t head_base = ((size_t)b * n_head + h) * S * HS;
 
-  // ---- before the dependency: pull this CTA's slice of the cache towards L2 (worst-case range)
-  {
+  // input_pos and ring_start are inputs of the step (written by the host side long before), not
+  // products of the previous kernel: they may be read before the dependency is resolved.
+  const long long p = input_pos[0];
+  const int w_slot = (int)(p < S ? p : (long long)S - 1);  // logical slot of the new token
+  const int L = w_slot + 1;                                 // valid logical slots 0..L-1
+  const int n_active = (L + FD_CHUNK - 1) / FD_CHUNK;
+  const int ring = *ring_start;
+  // ---- before the dependency: pull this CTA's valid, already-written rows of the cache towards L2
+  if (sp < n_active) {
     const int j0 = sp * FD_CHUNK;
-    const int nrows = min(FD_CHUNK, S - j0);
-    // physical rows are the logical ones rotated by the ring; prefetching the unrotated range is a
-    // hint only (exact when the ring has not started, i.e. always before the cache is full)
+    const int nrows = min(FD_CHUNK, L - 1 - j0);  // slot L-1 is written by this step
     for (int i = threadIdx.x; i < nrows * 2; i += blockDim.x) {
-      const char* pk = reinterpret_cast<const char*>(k_cache + head_base + (size_t)(j0 + (i >> 1)) * HS) + (i & 1) * 128;
-      const char* pv = reinterpret_cast<const char*>(v_cache + head_base + (size_t)(j0 + (i >> 1)) * HS) + (i & 1) * 128;
+      int phys = j0 + (i >> 1) + ring; if (phys >= S) phys -= S;
+      const char* pk = reinterpret_cast<const char*>(k_cache + head_base + (size_t)phys * HS) + (i & 1) * 128;
+      const char* pv = reinterpret_cast<const char*>(v_cache + head_base + (size_t)phys * HS) + (i & 1) * 128;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(pk));
       asm volatile("prefetch.global.L2 [%0];" ::"l"(pv));
     }
   }
   pdl_wait();
+  if (threadIdx.x == 0) tl_max(tl, 1);
   pdl_launch_dependents();  // attn.c_proj may start streaming its weights
 
-  const long long p = input_pos[0];
-  const int w_slot = (int)(p < S ? p : (long long)S - 1);  // logical slot of the new token
-  const int L = w_slot + 1;                                 // valid logical slots 0..L-1
-  const int n_active = (L + FD_CHUNK - 1) / FD_CHUNK;
   if (sp >= n_active) return;
-  const int ring = *ring_start;
   const long long prow = p < block_size ? p : (long long)block_size - 1;
   const int j0 = sp * FD_CHUNK, j1 = min(L, j0 + FD_CHUNK);
 
@@ -309,34 +312,45 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
     __syncthreads();  // the appended row is read below by this CTA
   }
 
+  if (threadIdx.x == 0) tl_max(tl, 2);
   float m = -INFINITY, l = 0.f, acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int jj = j0 + warp * 4; jj < j1; jj += FD_WARPS * 4) {  // warp-uniform trip count
-    const int j = jj + grp;
-    const bool valid = j < j1;
-    int phys = (valid ? j : j1 - 1) + ring; if (phys >= S) phys -= S;
-    const uint4* kr = reinterpret_cast<const uint4*>(k_cache + head_base + (size_t)phys * HS + d0);
-    const uint4* vr = reinterpret_cast<const uint4*>(v_cache + head_base + (size_t)phys * HS + d0);
-    const uint4 k0 = kr[0], k1 = kr[1], v0 = vr[0], v1 = vr[1];
-    float kf[16], vf[16];
-    bf16x8_to_f32(k0, kf); bf16x8_to_f32(k1, kf + 8);
-    float sc = 0.f;
+  // two independent 4-key batches per iteration: all four 16-byte loads of both are issued before use
+  for (int jj = j0 + warp * 8; jj < j1; jj += FD_WARPS * 8) {  // warp-uniform trip count
+    uint4 kq[2][2], vq[2][2];
+    bool valid[2];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sc = fmaf(q[i], kf[i], sc);
-    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-    if (valid) {
-      bf16x8_to_f32(v0, vf); bf16x8_to_f32(v1, vf + 8);
-      const float mn = fmaxf(m, sc);
-      const float corr = __expf(m - mn), pj = __expf(sc - mn);
-      l = l * corr + pj;
+    for (int u = 0; u < 2; ++u) {
+      const int j = jj + u * 4 + grp;
+      valid[u] = j < j1;
+      int phys = (valid[u] ? j : j1 - 1) + ring; if (phys >= S) phys -= S;
+      const uint4* kr = reinterpret_cast<const uint4*>(k_cache + head_base + (size_t)phys * HS + d0);
+      const uint4* vr = reinterpret_cast<const uint4*>(v_cache + head_base + (size_t)phys * HS + d0);
+      kq[u][0] = kr[0]; kq[u][1] = kr[1]; vq[u][0] = vr[0]; vq[u][1] = vr[1];
+    }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = fmaf(pj, vf[i], acc[i] * corr);
-      m = mn;
+    for (int u = 0; u < 2; ++u) {
+      float kf[16], vf[16];
+      bf16x8_to_f32(kq[u][0], kf); bf16x8_to_f32(kq[u][1], kf + 8);
+      float sc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sc = fmaf(q[i], kf[i], sc);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+      if (valid[u]) {
+        bf16x8_to_f32(vq[u][0], vf); bf16x8_to_f32(vq[u][1], vf + 8);
+        const float mn = fmaxf(m, sc);
+        const float corr = __expf(m - mn), pj = __expf(sc - mn);
+        l = l * corr + pj;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(pj, vf[i], acc[i] * corr);
+        m = mn;
+      }
     }
   }
+  if (threadIdx.x == 0) tl_max(tl, 3);
   // merge the 4 key groups of the warp (lanes with the same `sub` hold the same dims)
 #pragma unroll
   for (int off = 8; off <= 16; off <<= 1) {
@@ -372,18 +386,20 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
     wgt[w] = (sm_m[w] == -INFINITY) ? 0.f : __expf(sm_m[w] - M);
     Ls += sm_l[w] * wgt[w];
   }
-  const int d = threadIdx.x;  // 128 threads == HS
+  const int d = threadIdx.x & (HS - 1);  // threads >= HS duplicate the arithmetic and do not store
+  const bool writer = threadIdx.x < HS;
   float a = 0.f;
 #pragma unroll
   for (int w = 0; w < FD_WARPS; ++w) a += sm_acc[w][d] * wgt[w];
 
   if (n_active == 1) {  // nothing to merge
-    y[(size_t)b * C + h * HS + d] = f2bf(a / Ls);
+    if (writer) y[(size_t)b * C + h * HS + d] = f2bf(a / Ls);
+    if (threadIdx.x == 0) tl_max(tl, 4);
     return;
   }
   float* out = work + ((size_t)bh * n_split + sp) * (HS + 2);
-  if (d == 0) { out[0] = M; out[1] = Ls; }
-  out[2 + d] = a;
+  if (threadIdx.x == 0) { out[0] = M; out[1] = Ls; }
+  if (writer) out[2 + d] = a;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -404,8 +420,12 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
     LL += __ldcg(base + (size_t)s2 * (HS + 2) + 1) * wg;
     aa += __ldcg(base + (size_t)s2 * (HS + 2) + 2 + d) * wg;
   }
-  y[(size_t)b * C + h * HS + d] = f2bf(aa / LL);
+  if (writer) y[(size_t)b * C + h * HS + d] = f2bf(aa / LL);
+  if (threadIdx.x == 0) tl_max(tl, 4);
 }
+
+// debug timeline slot for the next fused-attention launch (set by b2l_decode_step; nullptr = off)
+void* g_attn_timeline = nullptr;
 
 static inline void split_plan(int T, int S, int* n_split, int* chunk) {
   if (T > 1) { *n_split = 1; *chunk = S; return; }
@@ -468,7 +488,7 @@ extern "C" int b2l_attention(void* qkv, void* k_cache, void* v_cache, const void
     LaunchCfg lc(dim3(B * n_head, n_split), dim3(FD_WARPS * 32), 0, st, (flags & B2L_F_PDL) != 0);
     B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, attn_decode_fused_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_cache,
                                 (__nv_bfloat16*)v_cache, (const float*)rope, input_pos, ring_start, (__nv_bfloat16*)y,
-                                (float*)work, tickets, n_head, S, block_size, n_split));
+                                (float*)work, tickets, n_head, S, block_size, n_split, (unsigned long long*)g_attn_timeline));
     return 0;
   }
   int rt = head_size / 2 < 32 ? 32 : head_size / 2;

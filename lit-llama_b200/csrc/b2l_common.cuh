@@ -79,6 +79,20 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return warp_sum(t);
 }
 
+// Debug timeline (tools/diag.py `timeline`): per-launch uint64[8] of %globaltimer nanoseconds,
+// slot 0 = min over CTAs (start), slots 1.. = max over CTAs.  nullptr = off.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tl_min(unsigned long long* tr, int slot) {
+  if (tr != nullptr) atomicMin(tr + slot, globaltimer_ns());
+}
+__device__ __forceinline__ void tl_max(unsigned long long* tr, int slot) {
+  if (tr != nullptr) atomicMax(tr + slot, globaltimer_ns());
+}
+
 // Programmatic dependent launch (PDL) device side.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {

@@ -23,6 +23,8 @@
 // lane (g = lane/4, t = lane%4) holds the A fragment of k16 chunk c: nibble s (s < 4) is row
 // g + 8*(s&1), k = 64*kb + 16*c + 2*t + 8*(s>>1); nibble s+4 is the same row at k+1.  So
 // ((w >> 4s) & 0x000f000f) | 0x43004300 is register a_s of mma.m16n8k16 as bf16 (128 + level).
+#include <cstdlib>
+
 #include "b2l_common.cuh"
 
 namespace b2l {
@@ -32,8 +34,10 @@ constexpr int RB = 16;                        // rows per row block
 constexpr int KB = 64;                        // k per k block (4 MMAs)
 constexpr int KB_BYTES = 512;                 // one (row block, k block): 32 lanes x 16 B
 constexpr int NCW = 8;                        // consumer warps
-constexpr int KB_PER_STAGE = 32;              // 16 KB per stage, 4 k blocks per warp
-constexpr int STAGE_BYTES = KB_PER_STAGE * KB_BYTES;
+constexpr int KBP_PER_STAGE = 16;             // k-block positions per stage (2 per consumer warp)
+constexpr int MAX_HALVES = 2;                 // a unit is one or two consecutive 16-row blocks sharing the B fragments
+constexpr int HALF_STAGE_BYTES = KBP_PER_STAGE * KB_BYTES;   // 8 KB
+constexpr int STAGE_BYTES = MAX_HALVES * HALF_STAGE_BYTES;   // 16 KB
 constexpr int MAX_STAGES = 6;
 constexpr int PRODUCER_WARP = NCW;            // warp 8
 constexpr int NTHREADS = (NCW + 2) * 32;      // 320
@@ -48,6 +52,7 @@ struct Params {
   int prologue; const __nv_bfloat16* norm_scale; float eps;
   int epilogue; const __nv_bfloat16* res;
   int nst;               // ring stages
+  unsigned long long* tl;  // debug timeline (nullptr = off)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,7 +121,7 @@ __host__ __device__ inline SmemLayout smem_layout(int nst, int K) {
   uint32_t o = 0;
   L.ring = o;    o += (uint32_t)nst * STAGE_BYTES;
   L.xf = o;      o += (uint32_t)(K / KB) * 128;       // B fragments: [k block][t (4)][32 B]
-  L.scratch = o; o += 2 * NCW * RB * 4;               // [buf][warp][row] fp32 partials
+  L.scratch = o; o += 2 * NCW * RB * MAX_HALVES * 4;  // [buf][warp][half][row] fp32 partials
   L.red = o;     o += 64;                             // per-warp reduction scratch + sum(x)
   o = (o + 7u) & ~7u;
   L.bars = o;    o += 2 * MAX_STAGES * 8;
@@ -124,17 +129,28 @@ __host__ __device__ inline SmemLayout smem_layout(int nst, int K) {
   return L;
 }
 
+// (w >> shift) & 0x000f000f | 0x43004300 in one LOP3: mask and magic live in registers
+__device__ __forceinline__ uint32_t lop_and_or(uint32_t a, uint32_t mask, uint32_t magic) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
+  return d;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const SmemLayout L = smem_layout(p.nst, p.K);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_kb = p.K / KB;                                           // k blocks per row block
-  const int stages_per_rb = (n_kb + KB_PER_STAGE - 1) / KB_PER_STAGE;  // last stage of a row block may be short
-  const int my_rbs = (p.n_rb > (int)blockIdx.x) ? (p.n_rb - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int total_stages = my_rbs * stages_per_rb;
+  const int n_kb = p.K / KB;                                              // k blocks per 16-row block
+  const int stages_per_unit = (n_kb + KBP_PER_STAGE - 1) / KBP_PER_STAGE;  // the last stage of a unit may be short
+  // this CTA's contiguous range of 16-row blocks, processed as pairs and at most one single
+  const int rb_lo = (int)(((long long)blockIdx.x * p.n_rb) / gridDim.x);
+  const int rb_hi = (int)(((long long)(blockIdx.x + 1) * p.n_rb) / gridDim.x);
+  const int n_units = (rb_hi - rb_lo + 1) / 2;
+  const int total_stages = n_units * stages_per_unit;
   const uint32_t bar_full = sbase + L.bars, bar_empty = bar_full + MAX_STAGES * 8;
 
+  if (tid == 0) tl_min(p.tl, 0);
   if (tid == 0) {
     for (int i = 0; i < p.nst; ++i) {
       mbar_init(bar_full + i * 8, 1);
@@ -145,20 +161,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
   __syncthreads();
 
   if (warp == PRODUCER_WARP) {
-    // ===================== TMA producer: the CTA's row blocks, stage by stage =====================
+    // ===================== TMA producer: the CTA's units, stage by stage =====================
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 1;  // fresh barriers: waiting on parity 1 passes immediately
       int it = 0;
-      for (int r = 0; r < my_rbs; ++r) {
-        const int rb = blockIdx.x + r * gridDim.x;
+      for (int u = 0; u < n_units; ++u) {
+        const int rb = rb_lo + 2 * u;
+        const int halves = min(2, rb_hi - rb);
         const uint8_t* src = p.qwt + (size_t)rb * n_kb * KB_BYTES;
-        for (int s = 0; s < stages_per_rb; ++s, ++it) {
-          const int nkb = min(KB_PER_STAGE, n_kb - s * KB_PER_STAGE);
+        for (int s = 0; s < stages_per_unit; ++s, ++it) {
+          const int nkb = min(KBP_PER_STAGE, n_kb - s * KBP_PER_STAGE);
           const uint32_t bytes = (uint32_t)nkb * KB_BYTES;
           mbar_wait(bar_empty + slot * 8, phase);
-          mbar_expect_tx(bar_full + slot * 8, bytes);
-          tma_bulk_g2s(sbase + L.ring + slot * STAGE_BYTES, src + (size_t)s * STAGE_BYTES, bytes, bar_full + slot * 8);
+          mbar_expect_tx(bar_full + slot * 8, bytes * halves);
+          for (int h = 0; h < halves; ++h)
+            tma_bulk_g2s(sbase + L.ring + slot * STAGE_BYTES + h * HALF_STAGE_BYTES,
+                         src + ((size_t)h * n_kb + (size_t)s * KBP_PER_STAGE) * KB_BYTES, bytes, bar_full + slot * 8);
           if (++slot == p.nst) { slot = 0; phase ^= 1; }
           if (it + 1 == min(total_stages, p.nst)) pdl_launch_dependents();  // ring full: next kernel may prefetch
         }
@@ -167,64 +186,82 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
     }
   } else if (warp < NCW) {
     // ===================== consumer warps =====================
-    pdl_wait();
-    float* red = reinterpret_cast<float*>(smem + L.red);
+    float* red = reinterpret_cast<float*>(smem + L.red);  // [0..7] sum of squares, [8..15] sum of x, per warp
     // ---- activations: [RMSNorm], B-fragment order, sum(x)
     {
       const bool norm = (p.prologue == B2L_PRO_RMSNORM);
       constexpr int NT = NCW * 32;   // 256 threads, 8 elements each per pass
       constexpr int MAXC = 6;        // up to 12288 elements in registers
       uint4 xv[MAXC], gv[MAXC];
+      // the RMSNorm scale is a weight: fetch it BEFORE waiting for the producing kernel (it comes from HBM,
+      // behind the queued weight prefetch; after the wait it would sit on the critical path)
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int k = (c * NT + tid) * 8;
+        gv[c] = make_uint4(0, 0, 0, 0);
+        if (norm && k < p.K) gv[c] = *reinterpret_cast<const uint4*>(p.norm_scale + k);
+      }
+      pdl_wait();
+      if (tid == 0) tl_max(p.tl, 1);
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         const int k = (c * NT + tid) * 8;
         xv[c] = make_uint4(0, 0, 0, 0);
-        gv[c] = make_uint4(0, 0, 0, 0);
-        if (k < p.K) {
-          xv[c] = *reinterpret_cast<const uint4*>(p.x + k);
-          if (norm) gv[c] = *reinterpret_cast<const uint4*>(p.norm_scale + k);
-        }
+        if (k < p.K) xv[c] = *reinterpret_cast<const uint4*>(p.x + k);
       }
+      const int nchunk = (p.K + NT * 8 - 1) / (NT * 8);  // warp-uniform: chunks that hold data
       float rinv = 1.f;
+      if (p.tl != nullptr) {  // debug: when did the activation loads land?
+        uint32_t sink = 0;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) sink |= xv[c].x;
+        if (tid == 0 && sink != 0x12345678u) tl_max(p.tl, 5);
+      }
+      // bf16x2 arithmetic: one HMUL2 is the exactly-rounded bf16 product the reference computes
+      // (bf16 * bf16 is exact in fp32, so rounding the fp32 product once == the packed multiply)
       if (norm) {
         float ss = 0.f;
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
-          const uint32_t w[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+          if (c < nchunk) {
+            const uint32_t w[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float a = __uint_as_float(w[q] << 16), b = __uint_as_float(w[q] & 0xffff0000u);
-            ss += rbf(a * a) + rbf(b * b);
+            for (int q = 0; q < 4; ++q) {
+              const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+              const __nv_bfloat162 sq = __hmul2(v, v);
+              const uint32_t su = *reinterpret_cast<const uint32_t*>(&sq);
+              ss += __uint_as_float(su << 16) + __uint_as_float(su & 0xffff0000u);
+            }
           }
         }
         ss = warp_sum(ss);
         if (lane == 0) red[warp] = ss;
         named_bar_sync(1, NT);
+        if (tid == 0) tl_max(p.tl, 6);
         ss = 0.f;
 #pragma unroll
         for (int w = 0; w < NCW; ++w) ss += red[w];
         rinv = rms_rinv(ss, p.K, p.eps);
-        named_bar_sync(1, NT);
       }
+      const __nv_bfloat162 rinv2 = __float2bfloat162_rn(rinv);  // rinv is already a bf16 value
       float sx = 0.f;
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         const int k = (c * NT + tid) * 8;
-        if (k < p.K) {
+        if (c < nchunk && k < p.K) {
           uint32_t w[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
           if (norm) {
             const uint32_t g[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float a = rms_apply(__uint_as_float(w[q] << 16), rinv, __uint_as_float(g[q] << 16));
-              const float b = rms_apply(__uint_as_float(w[q] & 0xffff0000u), rinv, __uint_as_float(g[q] & 0xffff0000u));
-              sx += a + b;
-              w[q] = (__float_as_uint(a) >> 16) | (__float_as_uint(b) & 0xffff0000u);
+              const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+              const __nv_bfloat162 gg = *reinterpret_cast<const __nv_bfloat162*>(&g[q]);
+              const __nv_bfloat162 y2 = __hmul2(gg, __hmul2(v, rinv2));  // bf16(scale * bf16(x * rinv)), model.py:276-277
+              w[q] = *reinterpret_cast<const uint32_t*>(&y2);
             }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) sx += __uint_as_float(w[q] << 16) + __uint_as_float(w[q] & 0xffff0000u);
           }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sx += __uint_as_float(w[q] << 16) + __uint_as_float(w[q] & 0xffff0000u);
           // 8 consecutive k = half of a k16 chunk: pair q (k = k0 + 2q, +1) is B register (half) of lane t = q
           // xf[k block][t][chunk c16 (4)][half (2)] u32
           const int kb = k >> 6, c16 = (k >> 4) & 3, half = (k >> 3) & 1;
@@ -234,46 +271,56 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
         }
       }
       sx = warp_sum(sx);
-      if (lane == 0) red[8 + warp] = sx;
-      named_bar_sync(1, NT);
-      if (tid == 0) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < NCW; ++w) t += red[8 + w];
-        red[7 + 9] = t;  // red[16]: sum over K of the (normalised) activations
-      }
-      named_bar_sync(3, NT + 32);  // releases the epilogue warp too: xf and sum(x) are ready
+      if (lane == 0) red[8 + warp] = sx;   // the epilogue warp adds the 8 partials in a fixed order
+      named_bar_sync(3, NT + 32);          // releases the epilogue warp too: xf and the partial sums are ready
+      if (tid == 0) tl_max(p.tl, 2);
     }
 
-    // ---- weights: stage -> registers -> mma.sync
+    // ---- weights: stage -> registers -> mma.sync.  Warp w takes k-block positions w and w + 8 of a stage
+    // and, for each, both 16-row halves of the unit (the B fragments are loaded once per position).
     const int t4 = lane & 3;
+    uint32_t kmask, kmagic;
+    asm volatile("mov.b32 %0, 0x000f000f;" : "=r"(kmask));
+    asm volatile("mov.b32 %0, 0x43004300;" : "=r"(kmagic));
     int slot = 0;
     uint32_t phase = 0;
     float* scratch = reinterpret_cast<float*>(smem + L.scratch);
-    for (int r = 0; r < my_rbs; ++r) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};  // two independent mma chains
-      for (int s = 0; s < stages_per_rb; ++s) {
-        const int nkb = min(KB_PER_STAGE, n_kb - s * KB_PER_STAGE);
-        mbar_wait(bar_full + slot * 8, phase);
-        const uint8_t* st_base = smem + L.ring + slot * STAGE_BYTES;
+    const uint8_t* xf_lane = smem + L.xf + t4 * 32;
+    for (int u = 0; u < n_units; ++u) {
+      const int halves = min(2, rb_hi - (rb_lo + 2 * u));
+      float acc[MAX_HALVES][2][4];
 #pragma unroll
-        for (int i = 0; i < KB_PER_STAGE / NCW; ++i) {
-          const int kbl = i * NCW + warp;  // k block inside the stage
+      for (int h = 0; h < MAX_HALVES; ++h)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[h][c][i] = 0.f;
+      for (int s = 0; s < stages_per_unit; ++s) {
+        const int nkb = min(KBP_PER_STAGE, n_kb - s * KBP_PER_STAGE);
+        mbar_wait(bar_full + slot * 8, phase);
+        const uint8_t* st_base = smem + L.ring + slot * STAGE_BYTES + lane * 16;
+#pragma unroll
+        for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
+          const int kbl = i * NCW + warp;  // k-block position inside the stage
           if (kbl < nkb) {
-            const uint4 wv = *reinterpret_cast<const uint4*>(st_base + kbl * KB_BYTES + lane * 16);
-            const uint4* xp = reinterpret_cast<const uint4*>(smem + L.xf + (s * KB_PER_STAGE + kbl) * 128 + t4 * 32);
+            const uint4* xp = reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * 128);
             const uint4 xa = xp[0], xb = xp[1];
-            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
             const uint32_t bb[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t a[4];
-              a[0] = (ww[c] & 0x000f000fu) | 0x43004300u;
-              a[1] = ((ww[c] >> 4) & 0x000f000fu) | 0x43004300u;
-              a[2] = ((ww[c] >> 8) & 0x000f000fu) | 0x43004300u;
-              a[3] = ((ww[c] >> 12) & 0x000f000fu) | 0x43004300u;
-              if (c & 1) mma_bf16_16816(acc1, a, bb[2 * c], bb[2 * c + 1]);
-              else mma_bf16_16816(acc, a, bb[2 * c], bb[2 * c + 1]);
+            for (int h = 0; h < MAX_HALVES; ++h) {
+              if (h < halves) {
+                const uint4 wv = *reinterpret_cast<const uint4*>(st_base + h * HALF_STAGE_BYTES + kbl * KB_BYTES);
+                const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  uint32_t a[4];
+                  a[0] = lop_and_or(ww[c], kmask, kmagic);
+                  a[1] = lop_and_or(ww[c] >> 4, kmask, kmagic);
+                  a[2] = lop_and_or(ww[c] >> 8, kmask, kmagic);
+                  a[3] = lop_and_or(ww[c] >> 12, kmask, kmagic);
+                  mma_bf16_16816(acc[h][c & 1], a, bb[2 * c], bb[2 * c + 1]);
+                }
+              }
             }
           }
         }
@@ -281,52 +328,63 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
         if (lane == 0) mbar_arrive(bar_empty + slot * 8);
         if (++slot == p.nst) { slot = 0; phase ^= 1; }
       }
-      // column 0 of the 16x8 result: lanes with t == 0 hold rows g (acc[0]) and g + 8 (acc[2])
-      const int buf = r & 1;
-      named_bar_sync(4 + buf, NCW * 32 + 32);  // epilogue warp has drained this scratch buffer (two row blocks ago)
+      // column 0 of each 16x8 result: lanes with t == 0 hold rows g (acc[.][0]) and g + 8 (acc[.][2])
+      const int buf = u & 1;
+      named_bar_sync(4 + buf, NCW * 32 + 32);  // the epilogue warp has drained this scratch buffer (two units ago)
       if (t4 == 0) {
-        scratch[(buf * NCW + warp) * RB + (lane >> 2)] = acc[0] + acc1[0];
-        scratch[(buf * NCW + warp) * RB + (lane >> 2) + 8] = acc[2] + acc1[2];
+#pragma unroll
+        for (int h = 0; h < MAX_HALVES; ++h) {
+          float* dst = scratch + ((buf * NCW + warp) * MAX_HALVES + h) * RB + (lane >> 2);
+          dst[0] = acc[h][0][0] + acc[h][1][0];
+          dst[8] = acc[h][0][2] + acc[h][1][2];
+        }
       }
       __syncwarp();
-      named_bar_arrive(6 + buf, NCW * 32 + 32);  // partials of this row block are in the scratch buffer
+      named_bar_arrive(6 + buf, NCW * 32 + 32);  // partials of this unit are in the scratch buffer
     }
+    if (tid == 0) tl_max(p.tl, 3);
   } else {
-    // ===================== epilogue warp =====================
+    // ===================== epilogue warp: lane = row of the 32-row unit =====================
     pdl_wait();
     const float* red = reinterpret_cast<const float*>(smem + L.red);
     const float* scratch = reinterpret_cast<const float*>(smem + L.scratch);
     named_bar_sync(3, NCW * 32 + 32);
-    const float sumx = red[16];
+    float sumx = 0.f;
+#pragma unroll
+    for (int w = 0; w < NCW; ++w) sumx += red[8 + w];  // sum over K of the (normalised) activations
     // both scratch buffers start free
-    named_bar_arrive(4, NCW * 32 + 32);
-    if (my_rbs > 1) named_bar_arrive(5, NCW * 32 + 32);
-    for (int r = 0; r < my_rbs; ++r) {
-      const int rb = blockIdx.x + r * gridDim.x;
-      const int buf = r & 1;
-      const int row = lane & 15;
-      const int o = min(rb * RB + row, p.N - 1);
+    if (n_units > 0) named_bar_arrive(4, NCW * 32 + 32);
+    if (n_units > 1) named_bar_arrive(5, NCW * 32 + 32);
+    for (int u = 0; u < n_units; ++u) {
+      const int rb = rb_lo + 2 * u;
+      const int halves = min(2, rb_hi - rb);
+      const int buf = u & 1;
+      const int half = lane >> 4, row = lane & 15;
+      const bool active = half < halves;
+      const int orow = (rb + half) * RB + row;             // row of the (interleaved) weight matrix
+      const int o = min(orow, p.N - 1);
       const float sc = load_sz(p.scales, p.szdt, o);
       const float zz = 128.0f + load_sz(p.zeros, p.szdt, o);
       float resv = 0.f;
-      if (p.epilogue == B2L_EPI_RESIDUAL && lane < 16 && rb * RB + row < p.N) resv = bf2f(p.res[rb * RB + row]);
+      if (p.epilogue == B2L_EPI_RESIDUAL && active && orow < p.N) resv = bf2f(p.res[orow]);
       named_bar_sync(6 + buf, NCW * 32 + 32);
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < NCW; ++w) t += scratch[(buf * NCW + w) * RB + row];  // fixed order: deterministic
-      if (r + 2 < my_rbs) named_bar_arrive(4 + buf, NCW * 32 + 32);               // scratch buffer free again
+      for (int w = 0; w < NCW; ++w) t += scratch[((buf * NCW + w) * MAX_HALVES + half) * RB + row];  // fixed order: deterministic
+      if (u + 2 < n_units) named_bar_arrive(4 + buf, NCW * 32 + 32);                                   // scratch buffer free again
       const float v = rbf(sc * (t - zz * sumx));
       if (p.epilogue == B2L_EPI_SWIGLU) {
-        // rows 0..7 of the block are c_fc1[o..o+7], rows 8..15 are c_fc2[o..o+7]
+        // rows 0..7 of a 16-row block are c_fc1[o..o+7], rows 8..15 are c_fc2[o..o+7]
         const float b = __shfl_down_sync(0xffffffffu, v, 8);
-        if (lane < 8) {
+        if (active && row < 8) {
           const float sl = rbf(v / (1.0f + expf(-v)));
-          p.y[rb * 8 + lane] = f2bf(sl * b);
+          p.y[(rb + half) * 8 + row] = f2bf(sl * b);
         }
-      } else if (lane < 16 && rb * RB + row < p.N) {
-        p.y[rb * RB + row] = f2bf(p.epilogue == B2L_EPI_RESIDUAL ? v + resv : v);
+      } else if (active && orow < p.N) {
+        p.y[orow] = f2bf(p.epilogue == B2L_EPI_RESIDUAL ? v + resv : v);
       }
     }
+    if (lane == 0) tl_max(p.tl, 4);
   }
 }
 
@@ -429,10 +487,15 @@ extern "C" int b2l_q4_gemv(const b2l_q4_linear_args* a, b2l_stream_t stream) {
   p.n_rb = (a->N + RB - 1) / RB;
   p.prologue = a->prologue; p.norm_scale = (const __nv_bfloat16*)a->norm_scale; p.eps = a->eps;
   p.epilogue = a->epilogue; p.res = (const __nv_bfloat16*)a->res;
+  p.tl = (unsigned long long*)a->trace;
+  // tuning knobs (read once): B2L_GEMV_CTAS_PER_SM (default 2), B2L_GEMV_STAGES (ring depth cap)
+  static const int env_cps = [] { const char* e = getenv("B2L_GEMV_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+  static const int env_nst = [] { const char* e = getenv("B2L_GEMV_STAGES"); return e ? atoi(e) : 0; }();
   // ring: as deep as fits two CTAs per SM
   const uint32_t fixed = smem_layout(0, a->K).total;
   int nst = (int)((110u * 1024u - fixed) / STAGE_BYTES);
   if (nst > MAX_STAGES) nst = MAX_STAGES;
+  if (env_nst > 0 && nst > env_nst) nst = env_nst;
   if (nst < 2) nst = 2;
   p.nst = nst;
   const SmemLayout L = smem_layout(nst, a->K);
@@ -441,7 +504,7 @@ extern "C" int b2l_q4_gemv(const b2l_q4_linear_args* a, b2l_stream_t stream) {
     B2L_CUDA(cudaFuncSetAttribute(q4_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     configured_smem = L.total;
   }
-  int grid = a->split_k > 0 ? a->split_k : 2 * sm_count();  // split_k doubles as a grid override for tuning
+  int grid = a->split_k > 0 ? a->split_k : (env_cps > 0 ? env_cps : 2) * sm_count();  // split_k doubles as a grid override
   if (grid > p.n_rb) grid = p.n_rb;
   LaunchCfg lc(dim3(grid), dim3(NTHREADS), L.total, (cudaStream_t)stream, (a->flags & B2L_F_PDL) != 0, 1);
   B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, q4_gemv_kernel, p));

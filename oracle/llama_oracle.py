@@ -216,7 +216,7 @@ def sdpa(q: Tensor, k: Tensor, v: Tensor, mask: Tensor) -> Tensor:
 @dataclass
 class QLin:
     """One linear layer of the model in whichever storage the mode uses."""
-    kind: str  # "dense" | "gptq" | "int8"
+    kind: str  # "dense" | "gptq" | "gptq_exact" | "int8"
     weight: Optional[Tensor] = None  # dense
     qw: Optional[Tensor] = None
     scales: Optional[Tensor] = None
@@ -231,6 +231,8 @@ class QLin:
             return torch.nn.functional.linear(x, self.weight)
         if self.kind == "gptq":
             return qlinear(x, self.qw, self.scales, self.zeros, self.bits, self.tile_cols)
+        if self.kind == "gptq_exact":  # arithmetic of the reference's GPU kernel: fp32 dequant, fp32+ accumulate
+            return qlinear_exact(x, self.qw, self.scales, self.zeros, self.bits, self.tile_cols).to(x.dtype)
         return int8_linear(x, self.cb, self.scb)
 
 
@@ -251,9 +253,11 @@ class OracleLLaMA:
 
     @staticmethod
     def from_state_dict(sd: Dict[str, Tensor], n_layer: int, n_head: int, block_size: int,
-                        mode: Optional[str] = None) -> "OracleLLaMA":
+                        mode: Optional[str] = None, exact_linears: bool = False) -> "OracleLLaMA":
         """Builds from a reference-format state dict (keys as produced by
-        lit_llama.model.LLaMA under utils.quantization(mode))."""
+        lit_llama.model.LLaMA under utils.quantization(mode)).  `exact_linears` selects the
+        arithmetic of the reference's GPU branch (quantization.py:259-269: fp32 dequant and
+        accumulate, no per-weight bf16 rounding) instead of its dense CPU branch (:392-423)."""
 
         def lin(prefix: str) -> QLin:
             if prefix + ".quant_weight" in sd:
@@ -264,7 +268,8 @@ class OracleLLaMA:
                 in_features = qw.shape[1] * epb
                 n_groups = sc.shape[1]
                 tile_cols = in_features if n_groups == 1 else -(-in_features // n_groups)
-                return QLin("gptq", qw=qw, scales=sc, zeros=sd[prefix + ".zeros"], bits=bits, tile_cols=tile_cols)
+                return QLin("gptq_exact" if exact_linears else "gptq", qw=qw, scales=sc, zeros=sd[prefix + ".zeros"], bits=bits,
+                            tile_cols=tile_cols)
             w = sd[prefix + ".weight"]
             if mode == "llm.int8":
                 cb, scb = int8_quantize_weight(w)

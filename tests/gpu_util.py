@@ -7,10 +7,10 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-from diag import rand_q4, ref_linear, relerr, tc_call, tile  # noqa: E402,F401
+from diag import gemv_call, rand_q4, ref_linear, relerr, tc_call, tile, tile_mma  # noqa: E402,F401
 
 
-def build_tiny(dev, cfg, mode="gptq.int4", seed=1234, tile_cols=-1):
+def build_tiny(dev, cfg, mode="gptq.int4", seed=1234, tile_cols=-1, exact_linears=False):
     import lit_llama_b200 as P
     from lit_llama_b200.utils import quantization
     from oracle import llama_oracle as O
@@ -24,5 +24,5 @@ def build_tiny(dev, cfg, mode="gptq.int4", seed=1234, tile_cols=-1):
     finally:
         torch.set_default_dtype(prev)
     model.load_state_dict(sd)
-    oracle = O.OracleLLaMA.from_state_dict(sd, cfg["n_layer"], cfg["n_head"], cfg["block_size"], mode)
+    oracle = O.OracleLLaMA.from_state_dict(sd, cfg["n_layer"], cfg["n_head"], cfg["block_size"], mode, exact_linears=exact_linears)
     return model.eval(), oracle, sd

@@ -25,9 +25,15 @@ def test_rmsnorm_and_rope_match_reference(dev):
     g = load_golden("ops.pt")
     n = P.RMSNorm(128).to(dev).bfloat16()
     n.scale.data = g["rms_scale"].bfloat16().to(dev)
-    y = n(g["rms_x"].bfloat16().to(dev)).cpu()
-    assert float((y == g["rms_y_bf16"]).float().mean()) > 0.995  # same rounding points; summation order may flip an ulp
-    torch.testing.assert_close(y.float(), g["rms_y_bf16"].float(), rtol=2 ** -7, atol=1e-6)
+    xg = g["rms_x"].bfloat16().to(dev)
+    y = n(xg).cpu()
+    # vs the reference run on the CPU: two bf16 ulps (torch's CPU mean rounds the sum to bf16 before
+    # dividing, its CUDA mean does not - the reference itself differs between devices here)
+    torch.testing.assert_close(y.float(), g["rms_y_bf16"].float(), rtol=2 ** -6, atol=1e-6)  # two bf16 ulps
+    # vs the reference formula (model.py:270-277) evaluated by torch on THIS device in bf16: same rounding points
+    ms = torch.mean(xg * xg, dim=-1, keepdim=True)
+    yt = (n.scale.data * (xg * torch.rsqrt(ms + 1e-5))).cpu()
+    assert float((y == yt).float().mean()) > 0.995
     yr = P.apply_rope(g["rope_x"].bfloat16().to(dev), g["rope_table_64x32"].to(dev)).cpu()
     assert torch.equal(yr, g["rope_y_bf16"])  # fp32 products and sums in the reference's order: bit-exact
     tab = P.build_rope_cache(64, 32, torch.int64, dev)
@@ -107,7 +113,10 @@ def test_generate_matches_reference_tokens(dev):
     first = int(P.generate(model, prompt, 1, top_k=1)[-1])
     model.reset_cache()
     out = P.generate(model, prompt, 5, top_k=1, eos_id=first)
-    assert out.tolist() == prompt.tolist() + [first]
+    # generate.py:88-89 returns idx[:input_pos] with input_pos == position of the eos token, i.e. the
+    # prompt only (the reference's comment says "include the EOS token"; its slice does not) - mirrored
+    assert out.tolist() == prompt.tolist()
+    assert torch.equal(out.cpu(), O.generate(oracle, prompt.cpu(), 5, top_k=1, eos_id=first))
 
 
 def test_fast_path_equals_module_path(dev):
@@ -127,24 +136,71 @@ def test_fast_path_equals_module_path(dev):
 
 
 def test_7b_shaped_block_vs_oracle(dev):
-    """One Block + lm_head at the BASELINE 7B widths (n_embd 4096, 32 heads, n_hidden
-    11008, vocab 32000): prefill 5 tokens then 2 decode steps, against the oracle."""
+    """One Block + lm_head at the BASELINE 7B widths (n_embd 4096, 32 heads of 128, n_hidden
+    11008, vocab 32000): prefill 5 tokens (tcgen05 kernel, prefill attention) then 3 decode
+    steps (batch-1 kernel, fused attention), against the oracle in both of the reference's
+    arithmetics: its GPU branch (fp32 dequant) tightly, its dense CPU branch (bf16-rounded
+    weights, ~1e-3 noise per linear) loosely."""
     from gpu_util import build_tiny
 
     cfg = dict(block_size=32, vocab_size=32000, n_layer=1, n_head=32, n_embd=4096)
-    model, oracle, _ = build_tiny(dev, cfg, seed=11)
+    model, exact, sd = build_tiny(dev, cfg, seed=11, exact_linears=True)
+    dense = O.OracleLLaMA.from_state_dict(sd, 1, 32, 32, "gptq.int4")
     prompt = torch.tensor([[5, 100, 31999, 7, 2048]])
     S = 8
     with torch.no_grad():
         got = [model(prompt.to(dev), S, torch.arange(5, device=dev))]
-        want = [oracle.forward(prompt, S, torch.arange(5))]
-        for i, t in enumerate([77, 12345]):
+        want = [exact.forward(prompt, S, torch.arange(5))]
+        loose = [dense.forward(prompt, S, torch.arange(5))]
+        for i, t in enumerate([77, 12345, 9]):
             got.append(model(torch.tensor([[t]], device=dev), S, torch.tensor([5 + i], device=dev)))
-            want.append(oracle.forward(torch.tensor([[t]]), S, torch.tensor([5 + i])))
-    for a, b in zip(got, want):
-        a, b = a.float().cpu(), b.float()
-        assert (a - b).norm() / b.norm() < 2e-2  # the oracle's dense path rounds every weight to bf16
-        torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2)
+            want.append(exact.forward(torch.tensor([[t]]), S, torch.tensor([5 + i])))
+            loose.append(dense.forward(torch.tensor([[t]]), S, torch.tensor([5 + i])))
+    for a, b, c in zip(got, want, loose):
+        a, b, c = a.float().cpu(), b.float(), c.float()
+        scale = b.abs().max()
+        # every module output is rounded to bf16 (2^-9 normwise each) on 4096..11008-wide vectors and
+        # single-ulp flips propagate through the next RMSNorm/linear: a percent normwise end to end
+        assert (a - b).norm() / b.norm() < 2e-2, float((a - b).norm() / b.norm())
+        assert (a - b).abs().max() < 0.05 * scale
+        assert (a - c).norm() / c.norm() < 3e-2
+    k, v = model.kv_caches[0]
+    torch.testing.assert_close(k[:, :, :8].float().cpu(), exact.kv[0][0].float(), rtol=2 ** -6, atol=2e-2)
+    torch.testing.assert_close(v[:, :, :8].float().cpu(), exact.kv[0][1].float(), rtol=2 ** -6, atol=2e-2)
+
+
+def test_fused_attention_equals_unfused(dev):
+    """head_size 128 single-token attention: the fused kernel (rope + append + split-S +
+    ticketed merge) against the three-kernel path on identical inputs, at several positions
+    including a full cache and the roll branch."""
+    from lit_llama_b200 import _lib as L
+
+    B, nh, hs, S, blk = 2, 8, 128, 300, 512
+    C = nh * hs
+    lib = L.lib()
+    g = torch.Generator(device=dev).manual_seed(3)
+    rope = O.rope_table(blk, hs).to(dev)
+    kc = (torch.randn(B, nh, S, hs, device=dev, generator=g) * 0.5).bfloat16()
+    vc = (torch.randn(B, nh, S, hs, device=dev, generator=g) * 0.5).bfloat16()
+    for pos, ring0 in [(0, 0), (5, 0), (127, 0), (128, 0), (299, 0), (300, 0), (333, 7)]:
+        qkv = torch.randn(B, 1, 3 * C, device=dev, generator=g).bfloat16()
+        outs = []
+        for flags in (0, 8):
+            k1, v1, q1 = kc.clone(), vc.clone(), qkv.clone()
+            ring = torch.tensor([ring0], dtype=torch.int32, device=dev)
+            p = torch.tensor([pos], dtype=torch.int64, device=dev)
+            L.check(lib.b2l_ring_advance(p.data_ptr(), 1, ring.data_ptr(), S, L.stream_ptr()), "ring")
+            work = torch.zeros(lib.b2l_attn_workspace_bytes(B, nh, hs, 1, S) // 4 + 1, device=dev, dtype=torch.float32)
+            y = torch.empty(B, 1, C, device=dev, dtype=torch.bfloat16)
+            for rep in range(2 if flags == 0 else 1):  # fused path twice: its ticket counters must re-arm themselves
+                rc = lib.b2l_attention(q1.data_ptr(), k1.data_ptr(), v1.data_ptr(), rope.data_ptr(), p.data_ptr(), ring.data_ptr(),
+                                       y.data_ptr(), work.data_ptr(), B, 1, nh, hs, S, blk, flags, L.stream_ptr())
+                assert rc == 0, lib.b2l_last_error()
+            torch.cuda.synchronize()
+            outs.append((y, k1, v1))
+        (yf, kf, vf), (yu, ku, vu) = outs
+        assert torch.equal(kf, ku) and torch.equal(vf, vu), pos      # appended rows bit-identical
+        torch.testing.assert_close(yf.float(), yu.float(), rtol=2 ** -7, atol=2e-3)
 
 
 def test_batched_decode_rows_are_independent(dev):

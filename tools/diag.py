@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "trace", "bench_layers", "bench_gemv", "bench_step"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "trace", "bench_layers", "bench_gemv", "bench_step", "timeline"]
 
 
 def rand_q4(N, K, dev, seed=0, sz_dtype=None, groups=1, bits=4):
@@ -573,6 +573,46 @@ def sec_bench_step():
                 torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / 60 * 1e3
             print(f"decode step 7B pos~16-80 pdl={pdl} graph={graph_after > 0}: {us:.1f} us/token  {1e6 / us:.1f} tok/s")
+
+
+def sec_timeline():
+    """%globaltimer stamps of every launch of one eager decode step (7B): who overlaps whom."""
+    import torch
+    from bench import build_synthetic_model
+
+    dev = torch.device("cuda")
+    model = build_synthetic_model("7B", dev)
+    S = 2048
+    model.graph_after = 0
+    model.copy_logits = False
+    pos0 = int(os.environ.get("B2L_TL_POS", "64"))
+    with torch.no_grad():
+        model(torch.randint(0, 32000, (1, 16), device=dev, dtype=torch.int32), S, torch.arange(16, device=dev))
+        tok = torch.randint(0, 32000, (1, 1), device=dev, dtype=torch.int32)
+        for pdl in (1, 0):
+            model.decode_flags = pdl
+            model._decode = None
+            for i in range(3):
+                model(tok, S, torch.tensor([pos0 + i], device=dev))
+            st = model._decode
+            n = 5 * model.config.n_layer + 1
+            tl = torch.zeros((n, 8), dtype=torch.int64, device=dev)
+            tl[:, 0] = 2**62
+            st.args.timeline = tl.data_ptr()
+            model(tok, S, torch.tensor([pos0 + 3], device=dev))
+            torch.cuda.synchronize()
+            st.args.timeline = None
+            t = tl.cpu()
+            names = ["c_attn", "attn", "c_proj", "fc12", "mlp_proj"]
+            base = int(t[5 * 4, 0])
+            print(f"--- pdl={pdl} pos={pos0 + 3}: layers 4-5, ns relative to layer 4 c_attn start; "
+                  "start(min) | wait_done(max) | x_ready(max) | loop_done(max) | end(max) | x_loaded(tid0) | after_ss_bar(tid0)")
+            for li in range(5 * 4, 5 * 6 + 1):
+                r = [int(v) - base if int(v) not in (0, 2**62) else None for v in t[li, :7]]
+                print(f"  L{li // 5} {names[li % 5]:9s} {r}")
+            tot = int(t[n - 1, 4]) - int(t[0, 0])
+            print(f"  whole step (first start -> lm_head end): {tot / 1e3:.1f} us; layer 4 start -> layer 5 start: "
+                  f"{(int(t[25, 0]) - int(t[20, 0])) / 1e3:.2f} us")
 
 
 def main():

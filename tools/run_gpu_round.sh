@@ -1,3 +1,3 @@
-mkdir -p gpurun_out
-timeout 900 python tools/diag.py gemv model bench_gemv bench_step > gpurun_out/diag4.log 2>&1
-cat gpurun_out/diag4.log | head -150
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+timeout 300 python tools/diag.py timeline 2>&1 | grep -v "^\[" | head -16
+timeout 300 python tools/diag.py bench_step 2>&1 | grep "decode step" | head -2
