@@ -118,9 +118,14 @@ class ClockSampler:
 
 
 def sample_next(logits, top_k=TOP_K, temperature=TEMPERATURE):
-    """generate.py:68-76."""
+    """generate.py:68-76 as lit_llama_b200.generate() runs it on the GPU (fused temperature /
+    top-k / softmax kernel + torch.multinomial); the CPU baseline keeps the reference's torch ops."""
     import torch
 
+    if logits.is_cuda:
+        from lit_llama_b200 import sample_probs
+
+        return torch.multinomial(sample_probs(logits[0, -1], temperature, top_k), num_samples=1)
     logits = logits[0, -1] / temperature
     v, _ = torch.topk(logits, min(top_k, logits.size(-1)))
     logits = torch.where(logits < v[[-1]], -float("Inf"), logits)

@@ -111,7 +111,8 @@ enum {
   B2L_F_NO_ALIAS_N = 2, /* debug: do not alias B operand rows 8..15 onto rows 0..7     */
   B2L_F_ROPE_ROWS = 4,  /* b2l_attention: `rope` holds the T rows already selected by
                            input_pos (the reference's call convention, model.py:93)    */
-  B2L_F_ATTN_UNFUSED = 8 /* debug: force the three-kernel attention path for T == 1    */
+  B2L_F_ATTN_UNFUSED = 8, /* debug: force the three-kernel attention path for T == 1   */
+  B2L_F_DEBUG_NOCOMPUTE = 16 /* debug: b2l_q4_gemv streams the weights but skips the math */
 };
 
 /* Fused [RMSNorm ->] int4 linear [-> residual | SwiGLU] on tcgen05.  Replaces
@@ -149,6 +150,13 @@ int b2l_silu_mul(const void* a, const void* b, void* y, size_t n, b2l_stream_t s
 
 /* x + h, model.py:166-167. */
 int b2l_add(const void* a, const void* b, void* y, size_t n, b2l_stream_t stream);
+
+/* generate.py:68-75 up to the probabilities: probs = softmax(where(l < kth, -inf, l)) with
+ * l = logits / temperature (bf16, rounded like ATen does on the GPU) and kth the top_k-th
+ * largest l (top_k == 0: no filtering).  logits, probs bf16 [V].  One launch; the caller draws
+ * with torch.multinomial so the RNG stream is the reference's. */
+int b2l_topk_softmax(const void* logits, float temperature, int top_k, void* probs, int V,
+                     b2l_stream_t stream);
 
 /* ------------------------------------------------------------------------------
  * CausalSelfAttention.forward without the two linears, model.py:197-232:

@@ -219,6 +219,12 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
   }
 }
 
+__device__ __forceinline__ uint32_t fd_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Dynamic shared memory: K tile [128 rows][128] bf16 (32 KB), V tile (32 KB), merge scratch.
+constexpr int FD_TILE_BYTES = FD_CHUNK * 128 * 2;
+constexpr int FD_SMEM_BYTES = 2 * FD_TILE_BYTES + FD_WARPS * 128 * 4 + 2 * FD_WARPS * 4 + 16;
+
 __global__ void __launch_bounds__(FD_WARPS * 32)
     attn_decode_fused_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ k_cache,
                              __nv_bfloat16* __restrict__ v_cache, const float* __restrict__ rope,
@@ -226,6 +232,15 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
                              __nv_bfloat16* __restrict__ y, float* __restrict__ work, int* __restrict__ tickets,
                              int n_head, int S, int block_size, int n_split, unsigned long long* tl) {
   constexpr int HS = 128;
+  extern __shared__ __align__(128) uint8_t fsm[];
+  __nv_bfloat16* kt = reinterpret_cast<__nv_bfloat16*>(fsm);
+  __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(fsm + FD_TILE_BYTES);
+  float* sm_acc = reinterpret_cast<float*>(fsm + 2 * FD_TILE_BYTES);              // [FD_WARPS][HS]
+  float* sm_m = sm_acc + FD_WARPS * HS;                                            // [FD_WARPS]
+  float* sm_l = sm_m + FD_WARPS;                                                   // [FD_WARPS]
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm_l + FD_WARPS);  // 8-byte aligned by construction
+  __shared__ int sm_last;
+
   if (threadIdx.x == 0) tl_min(tl, 0);
   const int bh = blockIdx.x, b = bh / n_head, h = bh % n_head, sp = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -238,29 +253,39 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   const int w_slot = (int)(p < S ? p : (long long)S - 1);  // logical slot of the new token
   const int L = w_slot + 1;                                 // valid logical slots 0..L-1
   const int n_active = (L + FD_CHUNK - 1) / FD_CHUNK;
+  if (sp >= n_active) return;
   const int ring = *ring_start;
-  // ---- before the dependency: pull this CTA's valid, already-written rows of the cache towards L2
-  if (sp < n_active) {
-    const int j0 = sp * FD_CHUNK;
-    const int nrows = min(FD_CHUNK, L - 1 - j0);  // slot L-1 is written by this step
-    for (int i = threadIdx.x; i < nrows * 2; i += blockDim.x) {
-      int phys = j0 + (i >> 1) + ring; if (phys >= S) phys -= S;
-      const char* pk = reinterpret_cast<const char*>(k_cache + head_base + (size_t)phys * HS) + (i & 1) * 128;
-      const char* pv = reinterpret_cast<const char*>(v_cache + head_base + (size_t)phys * HS) + (i & 1) * 128;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pk));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pv));
+  const int j0 = sp * FD_CHUNK, j1 = min(L, j0 + FD_CHUNK);
+  const int n_old = min(j1, L - 1) - j0;  // rows written by earlier steps (slot L-1 is written by this one)
+
+  // ---- before the dependency: TMA bulk copies of the old K/V rows of this chunk into shared memory
+  const uint32_t bar_a = fd_smem_u32(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (n_old > 0) {
+      int phys0 = j0 + ring; if (phys0 >= S) phys0 -= S;
+      const int first = min(n_old, S - phys0);  // rows before the ring wraps
+      const uint32_t total = (uint32_t)n_old * HS * 2 * 2;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(total) : "memory");
+      const __nv_bfloat16* ksrc = k_cache + head_base + (size_t)phys0 * HS;
+      const __nv_bfloat16* vsrc = v_cache + head_base + (size_t)phys0 * HS;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fd_smem_u32(kt)),
+                   "l"(ksrc), "r"((uint32_t)first * HS * 2), "r"(bar_a) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fd_smem_u32(vt)),
+                   "l"(vsrc), "r"((uint32_t)first * HS * 2), "r"(bar_a) : "memory");
+      if (first < n_old) {  // wrapped part starts at physical row 0
+        const uint32_t rest = (uint32_t)(n_old - first) * HS * 2;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fd_smem_u32(kt + (size_t)first * HS)),
+                     "l"(k_cache + head_base), "r"(rest), "r"(bar_a) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fd_smem_u32(vt + (size_t)first * HS)),
+                     "l"(v_cache + head_base), "r"(rest), "r"(bar_a) : "memory");
+      }
     }
   }
-  pdl_wait();
-  if (threadIdx.x == 0) tl_max(tl, 1);
-  pdl_launch_dependents();  // attn.c_proj may start streaming its weights
-
-  if (sp >= n_active) return;
+  // the RoPE row of this position is a constant table entry: fetch it before the dependency too
   const long long prow = p < block_size ? p : (long long)block_size - 1;
-  const int j0 = sp * FD_CHUNK, j1 = min(L, j0 + FD_CHUNK);
-
   const int grp = lane >> 3, sub = lane & 7, d0 = sub * 16;
-  // rope row for this lane's 8 pairs
   float cs[16];
   {
     const float4* rp = reinterpret_cast<const float4*>(rope + ((size_t)prow * (HS / 2) + d0 / 2) * 2);
@@ -270,6 +295,11 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
       cs[4 * i] = t.x; cs[4 * i + 1] = t.y; cs[4 * i + 2] = t.z; cs[4 * i + 3] = t.w;
     }
   }
+  __syncthreads();  // the barrier is initialised before anyone polls it
+  pdl_wait();
+  if (threadIdx.x == 0) tl_max(tl, 1);
+  pdl_launch_dependents();  // attn.c_proj may start streaming its weights
+
   const __nv_bfloat16* qrow = qkv + (size_t)b * 3 * C + h * HS + d0;
   float q[16];
   {
@@ -286,68 +316,65 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
       q[2 * i + 1] = o * scale;
     }
   }
-  // the CTA whose chunk holds the new slot appends k (rotated) and v
-  if (w_slot >= j0 && w_slot < j1) {
-    if (warp == 0 && grp == 0) {
-      int phys = w_slot + ring; if (phys >= S) phys -= S;
-      float raw[16];
-      bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + C), raw);
-      bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + C + 8), raw + 8);
-      uint32_t out[8];
+  // the CTA whose chunk holds the new slot appends k (rotated) and v: to the cache and to its tile
+  if (w_slot >= j0 && w_slot < j1 && warp == 0 && grp == 0) {
+    int phys = w_slot + ring; if (phys >= S) phys -= S;
+    float raw[16];
+    bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + C), raw);
+    bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + C + 8), raw + 8);
+    uint32_t out[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float c = cs[2 * i], s_ = cs[2 * i + 1];
-        const float e = __fsub_rn(__fmul_rn(raw[2 * i], c), __fmul_rn(raw[2 * i + 1], s_));
-        const float o = __fadd_rn(__fmul_rn(raw[2 * i + 1], c), __fmul_rn(raw[2 * i], s_));
-        out[i] = (__float_as_uint(rbf(e)) >> 16) | (__float_as_uint(rbf(o)) & 0xffff0000u);
-      }
-      uint4* kd = reinterpret_cast<uint4*>(k_cache + head_base + (size_t)phys * HS + d0);
-      kd[0] = make_uint4(out[0], out[1], out[2], out[3]);
-      kd[1] = make_uint4(out[4], out[5], out[6], out[7]);
-      const uint4* vs = reinterpret_cast<const uint4*>(qrow + 2 * C);
-      uint4* vd = reinterpret_cast<uint4*>(v_cache + head_base + (size_t)phys * HS + d0);
-      vd[0] = vs[0];
-      vd[1] = vs[1];
+    for (int i = 0; i < 8; ++i) {
+      const float c = cs[2 * i], s_ = cs[2 * i + 1];
+      const float e = __fsub_rn(__fmul_rn(raw[2 * i], c), __fmul_rn(raw[2 * i + 1], s_));
+      const float o = __fadd_rn(__fmul_rn(raw[2 * i + 1], c), __fmul_rn(raw[2 * i], s_));
+      out[i] = (__float_as_uint(rbf(e)) >> 16) | (__float_as_uint(rbf(o)) & 0xffff0000u);
     }
-    __syncthreads();  // the appended row is read below by this CTA
+    const uint4 ka = make_uint4(out[0], out[1], out[2], out[3]), kb2 = make_uint4(out[4], out[5], out[6], out[7]);
+    const uint4* vs = reinterpret_cast<const uint4*>(qrow + 2 * C);
+    const uint4 va = vs[0], vb = vs[1];
+    uint4* kd = reinterpret_cast<uint4*>(k_cache + head_base + (size_t)phys * HS + d0);
+    uint4* vd = reinterpret_cast<uint4*>(v_cache + head_base + (size_t)phys * HS + d0);
+    kd[0] = ka; kd[1] = kb2; vd[0] = va; vd[1] = vb;
+    uint4* ks = reinterpret_cast<uint4*>(kt + (size_t)(w_slot - j0) * HS + d0);
+    uint4* vsm = reinterpret_cast<uint4*>(vt + (size_t)(w_slot - j0) * HS + d0);
+    ks[0] = ka; ks[1] = kb2; vsm[0] = va; vsm[1] = vb;
   }
-
+  if (n_old > 0) {  // the bulk copies have landed
+    uint32_t ok;
+    do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar_a) : "memory");
+    } while (!ok);
+  }
+  __syncthreads();
   if (threadIdx.x == 0) tl_max(tl, 2);
+
   float m = -INFINITY, l = 0.f, acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  // two independent 4-key batches per iteration: all four 16-byte loads of both are issued before use
-  for (int jj = j0 + warp * 8; jj < j1; jj += FD_WARPS * 8) {  // warp-uniform trip count
-    uint4 kq[2][2], vq[2][2];
-    bool valid[2];
+  const int nrows = j1 - j0;
+  for (int rr = warp * 4; rr < nrows; rr += FD_WARPS * 4) {  // warp-uniform trip count; 8 lanes per key
+    const int r = rr + grp;
+    const bool valid = r < nrows;
+    const int rc = valid ? r : nrows - 1;
+    const uint4* kr = reinterpret_cast<const uint4*>(kt + (size_t)rc * HS + d0);
+    const uint4* vr = reinterpret_cast<const uint4*>(vt + (size_t)rc * HS + d0);
+    float kf[16], vf[16];
+    bf16x8_to_f32(kr[0], kf); bf16x8_to_f32(kr[1], kf + 8);
+    float sc = 0.f;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j = jj + u * 4 + grp;
-      valid[u] = j < j1;
-      int phys = (valid[u] ? j : j1 - 1) + ring; if (phys >= S) phys -= S;
-      const uint4* kr = reinterpret_cast<const uint4*>(k_cache + head_base + (size_t)phys * HS + d0);
-      const uint4* vr = reinterpret_cast<const uint4*>(v_cache + head_base + (size_t)phys * HS + d0);
-      kq[u][0] = kr[0]; kq[u][1] = kr[1]; vq[u][0] = vr[0]; vq[u][1] = vr[1];
-    }
+    for (int i = 0; i < 16; ++i) sc = fmaf(q[i], kf[i], sc);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+    if (valid) {
+      bf16x8_to_f32(vr[0], vf); bf16x8_to_f32(vr[1], vf + 8);
+      const float mn = fmaxf(m, sc);
+      const float corr = __expf(m - mn), pj = __expf(sc - mn);
+      l = l * corr + pj;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      float kf[16], vf[16];
-      bf16x8_to_f32(kq[u][0], kf); bf16x8_to_f32(kq[u][1], kf + 8);
-      float sc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) sc = fmaf(q[i], kf[i], sc);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-      if (valid[u]) {
-        bf16x8_to_f32(vq[u][0], vf); bf16x8_to_f32(vq[u][1], vf + 8);
-        const float mn = fmaxf(m, sc);
-        const float corr = __expf(m - mn), pj = __expf(sc - mn);
-        l = l * corr + pj;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = fmaf(pj, vf[i], acc[i] * corr);
-        m = mn;
-      }
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(pj, vf[i], acc[i] * corr);
+      m = mn;
     }
   }
   if (threadIdx.x == 0) tl_max(tl, 3);
@@ -368,13 +395,10 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
     m = mn;
   }
   // merge the warps through shared memory
-  __shared__ float sm_m[FD_WARPS], sm_l[FD_WARPS];
-  __shared__ float sm_acc[FD_WARPS][HS];
-  __shared__ int sm_last;
   if (lane == 0) { sm_m[warp] = m; sm_l[warp] = l; }
   if (grp == 0) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sm_acc[warp][d0 + i] = acc[i];
+    for (int i = 0; i < 16; ++i) sm_acc[warp * HS + d0 + i] = acc[i];
   }
   __syncthreads();
   float M = -INFINITY;
@@ -390,7 +414,7 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   const bool writer = threadIdx.x < HS;
   float a = 0.f;
 #pragma unroll
-  for (int w = 0; w < FD_WARPS; ++w) a += sm_acc[w][d] * wgt[w];
+  for (int w = 0; w < FD_WARPS; ++w) a += sm_acc[w * HS + d] * wgt[w];
 
   if (n_active == 1) {  // nothing to merge
     if (writer) y[(size_t)b * C + h * HS + d] = f2bf(a / Ls);
@@ -400,25 +424,41 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   float* out = work + ((size_t)bh * n_split + sp) * (HS + 2);
   if (threadIdx.x == 0) { out[0] = M; out[1] = Ls; }
   if (writer) out[2 + d] = a;
-  __threadfence();
-  __syncthreads();
+  __syncthreads();  // all partial stores of this CTA are ordered before the ticket (cumulative release below)
   if (threadIdx.x == 0) {
-    const int t = atomicAdd(&tickets[bh], 1);
+    int t;
+    asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(t) : "l"(tickets + bh) : "memory");
     sm_last = (t == n_active - 1);
     if (sm_last) tickets[bh] = 0;  // every contributor has arrived: safe to re-arm for the next step
   }
-  __syncthreads();
+  __syncthreads();  // thread 0's acquire + this barrier order the other CTAs' partials before the loads below
   if (!sm_last) return;
-  __threadfence();
+  // merge: every load is issued before the first use (n_split <= 16 for S <= 2048; larger S loops in batches)
   const float* base = work + (size_t)bh * n_split * (HS + 2);
-  float MM = -INFINITY;
-  for (int s2 = 0; s2 < n_active; ++s2) MM = fmaxf(MM, __ldcg(base + (size_t)s2 * (HS + 2)));
-  float LL = 0.f, aa = 0.f;
-  for (int s2 = 0; s2 < n_active; ++s2) {
-    const float ms = __ldcg(base + (size_t)s2 * (HS + 2));
-    const float wg = __expf(ms - MM);
-    LL += __ldcg(base + (size_t)s2 * (HS + 2) + 1) * wg;
-    aa += __ldcg(base + (size_t)s2 * (HS + 2) + 2 + d) * wg;
+  float MM = -INFINITY, LL = 0.f, aa = 0.f;
+  for (int s0 = 0; s0 < n_active; s0 += 16) {
+    float ms[16], ls[16], as[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int s2 = s0 + i;
+      const bool ok = s2 < n_active;
+      const float* bp = base + (size_t)(ok ? s2 : s0) * (HS + 2);
+      ms[i] = ok ? __ldcg(bp) : -INFINITY;
+      ls[i] = ok ? __ldcg(bp + 1) : 0.f;
+      as[i] = ok ? __ldcg(bp + 2 + d) : 0.f;
+    }
+    float bm = MM;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bm = fmaxf(bm, ms[i]);
+    const float c0 = (MM == -INFINITY) ? 0.f : __expf(MM - bm);
+    LL *= c0; aa *= c0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float wg = (ms[i] == -INFINITY) ? 0.f : __expf(ms[i] - bm);
+      LL += ls[i] * wg;
+      aa += as[i] * wg;
+    }
+    MM = bm;
   }
   if (writer) y[(size_t)b * C + h * HS + d] = f2bf(aa / LL);
   if (threadIdx.x == 0) tl_max(tl, 4);
@@ -485,7 +525,12 @@ extern "C" int b2l_attention(void* qkv, void* k_cache, void* v_cache, const void
   if (T == 1 && head_size == 128 && !(flags & B2L_F_ROPE_ROWS) && !(flags & B2L_F_ATTN_UNFUSED)) {
     const int n_split = (S + FD_CHUNK - 1) / FD_CHUNK;
     int* tickets = reinterpret_cast<int*>(reinterpret_cast<char*>(work) + ws_partials_bytes(B, n_head, head_size, T, S));
-    LaunchCfg lc(dim3(B * n_head, n_split), dim3(FD_WARPS * 32), 0, st, (flags & B2L_F_PDL) != 0);
+    static bool smem_set = false;
+    if (!smem_set) {
+      B2L_CUDA(cudaFuncSetAttribute(attn_decode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FD_SMEM_BYTES));
+      smem_set = true;
+    }
+    LaunchCfg lc(dim3(B * n_head, n_split), dim3(FD_WARPS * 32), FD_SMEM_BYTES, st, (flags & B2L_F_PDL) != 0);
     B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, attn_decode_fused_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_cache,
                                 (__nv_bfloat16*)v_cache, (const float*)rope, input_pos, ring_start, (__nv_bfloat16*)y,
                                 (float*)work, tickets, n_head, S, block_size, n_split, (unsigned long long*)g_attn_timeline));

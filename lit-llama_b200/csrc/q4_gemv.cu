@@ -53,6 +53,7 @@ struct Params {
   int epilogue; const __nv_bfloat16* res;
   int nst;               // ring stages
   unsigned long long* tl;  // debug timeline (nullptr = off)
+  int nocompute;           // debug: consumers release every stage untouched (pure TMA streaming rate)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
 #pragma unroll
         for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
           const int kbl = i * NCW + warp;  // k-block position inside the stage
-          if (kbl < nkb) {
+          if (kbl < nkb && !p.nocompute) {
             const uint4* xp = reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * 128);
             const uint4 xa = xp[0], xb = xp[1];
             const uint32_t bb[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
@@ -488,6 +489,7 @@ extern "C" int b2l_q4_gemv(const b2l_q4_linear_args* a, b2l_stream_t stream) {
   p.prologue = a->prologue; p.norm_scale = (const __nv_bfloat16*)a->norm_scale; p.eps = a->eps;
   p.epilogue = a->epilogue; p.res = (const __nv_bfloat16*)a->res;
   p.tl = (unsigned long long*)a->trace;
+  p.nocompute = (a->flags & B2L_F_DEBUG_NOCOMPUTE) ? 1 : 0;
   // tuning knobs (read once): B2L_GEMV_CTAS_PER_SM (default 2), B2L_GEMV_STAGES (ring depth cap)
   static const int env_cps = [] { const char* e = getenv("B2L_GEMV_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   static const int env_nst = [] { const char* e = getenv("B2L_GEMV_STAGES"); return e ? atoi(e) : 0; }();

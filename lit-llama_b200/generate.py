@@ -11,8 +11,21 @@ from typing import Optional
 
 import torch
 
+from . import _lib as L
 from .model import LLaMA
 from .utils import llama_model_lookup, quantization
+
+
+def sample_probs(logits_row: torch.Tensor, temperature: float = 1.0, top_k: Optional[int] = None) -> torch.Tensor:
+    """generate.py:68-75: probabilities of the next token from the last position's logits
+    (V,) bf16: temperature, top-k filter and softmax fused in one kernel (b2l_topk_softmax)."""
+    L.require_cuda_bf16(logits_row, "sample_probs")
+    x = logits_row.contiguous()
+    V = x.numel()
+    probs = torch.empty_like(x)
+    k = 0 if top_k is None else min(int(top_k), V)
+    L.check(L.lib().b2l_topk_softmax(x.data_ptr(), float(temperature), k, probs.data_ptr(), V, L.stream_ptr()), "b2l_topk_softmax")
+    return probs
 
 
 @torch.no_grad()
@@ -41,11 +54,7 @@ def generate(
     for _ in range(max_new_tokens):
         x = idx.index_select(0, input_pos).view(1, -1)
         logits = model(x, max_seq_length, input_pos)
-        logits = logits[0, -1] / temperature
-        if top_k is not None:
-            v, _ = torch.topk(logits, min(top_k, logits.size(-1)))
-            logits = torch.where(logits < v[[-1]], -float("Inf"), logits)
-        probs = torch.nn.functional.softmax(logits, dim=-1)
+        probs = sample_probs(logits[0, -1], temperature, top_k)  # generate.py:68-75 in one launch
         idx_next = torch.multinomial(probs, num_samples=1).to(dtype=dtype)
         input_pos = input_pos[-1:] + 1
         idx = idx.index_copy(0, input_pos, idx_next)

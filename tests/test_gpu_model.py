@@ -215,3 +215,24 @@ def test_batched_decode_rows_are_independent(dev):
         model(idx[1:], 16, torch.arange(3, device=dev))
         one = model(torch.tensor([[60]], device=dev), 16, torch.tensor([3], device=dev))
     torch.testing.assert_close(both[1:].float(), one.float(), rtol=RTOL, atol=ATOL)
+
+
+def test_fused_sampling_head_matches_torch_ops(dev):
+    """b2l_topk_softmax vs the reference's op sequence (generate.py:68-75) run by torch on the
+    same device: same kept set (incl. ties at the threshold), probabilities within one bf16 ulp."""
+    import lit_llama_b200 as P
+
+    g = torch.Generator(device=dev).manual_seed(0)
+    for V, k, temp in [(32000, 200, 0.8), (32000, 1, 1.0), (32000, None, 0.7), (128, 4, 2.0), (1000, 1000, 1.3), (50257, 50, 0.9)]:
+        logits = (torch.randn(V, device=dev, generator=g) * 3).bfloat16()
+        if V == 128:
+            logits[5] = logits[9]  # a tie
+        got = P.sample_probs(logits, temp, k)
+        ref = logits / temp
+        if k is not None:
+            v, _ = torch.topk(ref, min(k, V))
+            ref = torch.where(ref < v[[-1]], -float("Inf"), ref)
+        want = torch.nn.functional.softmax(ref, dim=-1)
+        assert torch.equal(got == 0, want == 0), (V, k)
+        torch.testing.assert_close(got.float(), want.float(), rtol=2 ** -7, atol=1e-8)
+        assert abs(float(got.float().sum()) - 1.0) < 2e-2
