@@ -151,6 +151,24 @@ int b2l_silu_mul(const void* a, const void* b, void* y, size_t n, b2l_stream_t s
 /* x + h, model.py:166-167. */
 int b2l_add(const void* a, const void* b, void* y, size_t n, b2l_stream_t stream);
 
+/* ------------------------------------------------------------------------------
+ * Linear8bitLt  (lit_llama/quantization.py:38-77; forward inherited from bitsandbytes:
+ * LLM.int8() with has_fp16_weights=False, threshold=6.0).  CB int8 (out, in) row-major,
+ * SCB fp32 (out) as produced by quantization.py:69-77.
+ * ---------------------------------------------------------------------------- */
+/* load-time re-tiling of CB into mma.m16n8k32 fragment order: [N/16][K/128][4][32 lanes][16 B] */
+size_t b2l_q8_tiled_bytes(int N, int K);
+int b2l_q8_tile(const void* cb, void* tiled, int N, int K, b2l_stream_t stream);
+/* y[N] (bf16) for ONE activation row x[K] (bf16): fp16 cast, outlier columns (|a| >= threshold)
+ * in fp16 against CB*SCB/127, the rest row-absmax-quantised to int8 and contracted on the tensor
+ * cores, dequantised by SCA*SCB/127^2.  outlier_mask: optional K-bit mask shared by a batch
+ * (b2l_q8_outlier_mask); NULL = derive it from this row. */
+int b2l_q8_gemv(const void* x, const void* w_tiled, const void* cb, const void* scb,
+                const void* outlier_mask, void* y, int N, int K, float threshold, int flags,
+                b2l_stream_t stream);
+int b2l_q8_outlier_mask(const void* x, int ldx, int M, int K, float threshold, void* mask,
+                        b2l_stream_t stream);
+
 /* generate.py:68-75 up to the probabilities: probs = softmax(where(l < kth, -inf, l)) with
  * l = logits / temperature (bf16, rounded like ATen does on the GPU) and kth the top_k-th
  * largest l (top_k == 0: no filtering).  logits, probs bf16 [V].  One launch; the caller draws

@@ -8,11 +8,12 @@ by hand-written CUDA in `csrc/` behind the C ABI of `include/b2l.h`.
 """
 from .model import LLaMA, LLaMAConfig, Block, CausalSelfAttention, MLP, RMSNorm, build_rope_cache, apply_rope
 from .quantization import ColBlockQuantizedLinear
+from .int8 import Linear8bitLt
 from .utils import find_multiple, llama_model_lookup
 from .generate import generate, sample_probs
 from .patch import patch_reference
 
 __all__ = [
     "LLaMA", "LLaMAConfig", "Block", "CausalSelfAttention", "MLP", "RMSNorm", "build_rope_cache", "apply_rope",
-    "ColBlockQuantizedLinear", "find_multiple", "llama_model_lookup", "generate", "sample_probs", "patch_reference",
+    "ColBlockQuantizedLinear", "Linear8bitLt", "find_multiple", "llama_model_lookup", "generate", "sample_probs", "patch_reference",
 ]

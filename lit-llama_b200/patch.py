@@ -36,6 +36,10 @@ def patch_reference(lit_llama_module=None):
             setattr(lit_llama_module, name, getattr(m, name))
     saved[("quant", "ColBlockQuantizedLinear")] = ref_quant.ColBlockQuantizedLinear
     ref_quant.ColBlockQuantizedLinear = q.ColBlockQuantizedLinear
+    from . import int8 as i8
+
+    saved[("quant", "Linear8bitLt")] = getattr(ref_quant, "Linear8bitLt", None)  # absent when bitsandbytes is not installed
+    ref_quant.Linear8bitLt = i8.Linear8bitLt
     saved[("quant", "qlinear_4bit_weight")] = getattr(ref_quant, "qlinear_4bit_weight", None)
     ref_quant.qlinear_4bit_weight = q.qlinear_4bit_weight
     saved[("utils", "quantization")] = ref_utils.quantization

@@ -15,7 +15,8 @@ def build_tiny(dev, cfg, mode="gptq.int4", seed=1234, tile_cols=-1, exact_linear
     from lit_llama_b200.utils import quantization
     from oracle import llama_oracle as O
 
-    sd = O.synth_state_dict(cfg["n_layer"], cfg["n_head"], cfg["n_embd"], cfg["vocab_size"], mode, dtype=torch.bfloat16, seed=seed)
+    sd = O.synth_state_dict(cfg["n_layer"], cfg["n_head"], cfg["n_embd"], cfg["vocab_size"], None if mode == "llm.int8" else mode,
+                            dtype=torch.bfloat16, seed=seed)  # llm.int8 loads a float checkpoint and quantises on load
     prev = torch.get_default_dtype()
     torch.set_default_dtype(torch.bfloat16)
     try:

@@ -236,3 +236,21 @@ def test_fused_sampling_head_matches_torch_ops(dev):
         assert torch.equal(got == 0, want == 0), (V, k)
         torch.testing.assert_close(got.float(), want.float(), rtol=2 ** -7, atol=1e-8)
         assert abs(float(got.float().sum()) - 1.0) < 2e-2
+
+
+def test_llm_int8_model_vs_oracle(dev):
+    """--quantize llm.int8: tiny model, prefill + decode, against the oracle restatement."""
+    from gpu_util import build_tiny
+
+    cfg = dict(block_size=32, vocab_size=96, n_layer=2, n_head=4, n_embd=128)
+    model, oracle, _ = build_tiny(dev, cfg, mode="llm.int8", seed=7)
+    prompt = torch.tensor([[3, 17, 40, 41, 2]])
+    with torch.no_grad():
+        got = [model(prompt.to(dev), 16, torch.arange(5, device=dev))]
+        want = [oracle.forward(prompt, 16, torch.arange(5))]
+        for i, t in enumerate([9, 60]):
+            got.append(model(torch.tensor([[t]], device=dev), 16, torch.tensor([5 + i], device=dev)))
+            want.append(oracle.forward(torch.tensor([[t]]), 16, torch.tensor([5 + i])))
+    for a, b in zip(got, want):
+        a, b = a.float().cpu(), b.float()
+        assert (a - b).norm() / b.norm() < 2e-2, float((a - b).norm() / b.norm())

@@ -120,7 +120,7 @@ def test_gemv_prologue_epilogue_and_determinism(dev):
     qt = tile_mma(L, qw, N, K)
     x = (torch.randn(1, K, device=dev) * 0.7).bfloat16()
     g = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
-    xn = O.rmsnorm(x.cpu(), g.cpu()).to(dev)
+    xn = g * (x * torch.rsqrt(torch.mean(x * x, dim=-1, keepdim=True) + 1e-5))  # model.py:270-277 in bf16 on this device
     y, err = gemv_call(L, x, qt, sc, z, N, K, prologue=1, norm_scale=g)
     assert err is None, err
     assert relerr(y, ref_linear(xn, lv, sc, z)) < 1e-3 + 2.0 ** -9
@@ -183,7 +183,8 @@ def test_tc_prologue_epilogue(dev):
     qt = tile(L, qw, N, K)
     x = (torch.randn(M, K, device=dev) * 0.7).bfloat16()
     g = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
-    xn = O.rmsnorm(x.cpu(), g.cpu()).to(dev)  # oracle RMSNorm (bf16 rounding points)
+    # the reference formula (model.py:270-277) in bf16 on this device (torch's CPU mean double-rounds, see test_gpu_model)
+    xn = g * (x * torch.rsqrt(torch.mean(x * x, dim=-1, keepdim=True) + 1e-5))
     y, err = tc_call(L, x, qt, sc, z, N, K, prologue=1, norm_scale=g, eps=1e-5)
     assert err is None, err
     assert relerr(y, ref_linear(xn, lv, sc, z)) < 1e-3 + 2.0 ** -9
@@ -211,3 +212,30 @@ def test_unsupported_shapes_raise(dev):
         lin(torch.zeros(1, 64, device=dev))  # fp32 activations: no silent fallback
     with pytest.raises(RuntimeError):
         lin(torch.zeros(1, 64, dtype=torch.bfloat16))  # CPU tensor
+
+
+@pytest.mark.parametrize("N,K,M,outliers", [(48, 256, 1, 0), (48, 256, 1, 3), (130, 1024, 3, 2), (4096, 4096, 1, 0), (4096, 4096, 1, 5),
+                                           (4096, 11008, 2, 1), (32000, 4096, 1, 0)])
+def test_int8_linear_vs_oracle(dev, N, K, M, outliers):
+    """Linear8bitLt (LLM.int8) through the C ABI vs the oracle restatement, with and without
+    outlier columns (|a| >= 6), batch-shared outlier mask for M > 1.  Parity unpinned (bitsandbytes
+    is not available): this checks the CUDA path against the published algorithm only."""
+    import lit_llama_b200 as P
+
+    g = torch.Generator().manual_seed(N + K + M + outliers)
+    w = torch.randn(N, K, generator=g) * 0.03
+    x = torch.randn(M, K, generator=g)
+    for i in range(outliers):
+        x[i % M, (37 * i + 11) % K] = 7.5 + i
+    lin = P.Linear8bitLt(K, N, bias=False)
+    lin.load_state_dict({"weight": w})
+    cb, scb = O.int8_quantize_weight(w)
+    assert torch.equal(lin.weight.CB, cb) and torch.equal(lin.weight.SCB, scb)
+    lin = lin.to(dev)
+    xb = x.bfloat16()
+    y = lin(xb.to(dev)).float().cpu()
+    want = O.int8_linear(xb, cb, scb).float()
+    exact = xb.float() @ w.t()
+    assert (y - want).norm() / want.norm() < 2e-3, float((y - want).norm() / want.norm())
+    torch.testing.assert_close(y, want, rtol=2 ** -6, atol=2e-2 * float(want.abs().max()) * 0.1 + 1e-3)
+    assert (y - exact).norm() / exact.norm() < 3e-2  # the int8 scheme itself is ~1% accurate
