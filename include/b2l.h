@@ -261,7 +261,7 @@ typedef struct b2l_decode_args {
   void* attn_work;           /* f32, b2l_attn_workspace_bytes                         */
   void* logits;              /* bf16 [B, vocab]                                       */
   int flags;                 /* B2L_F_*                                               */
-  void* timeline;            /* debug: device uint64[(5*n_layer+1)*8] of %globaltimer stamps per
+  void* timeline;            /* debug: device uint64[(5*n_layer+1)*64] of %globaltimer stamps per
                                 launch (NULL = off); tools/diag.py `timeline`           */
 } b2l_decode_args;
 

@@ -99,11 +99,11 @@ extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {
   const int C = d->n_embd, hs = C / d->n_head, B = d->B;
   const int fl = d->flags;
   int rc;
-  // debug timeline: launch i of the step writes uint64[8] at timeline + 64*i (order: per Block c_attn,
+  // debug timeline: launch i of the step writes uint64[64] at timeline + 512*i (order: per Block c_attn,
   // attention, c_proj, fc12, mlp_proj; then lm_head)
   char* tlb = (char*)d->timeline;
   int li = 0;
-  auto tl = [&]() -> void* { void* r = tlb ? (void*)(tlb + 64 * li) : nullptr; ++li; return r; };
+  auto tl = [&]() -> void* { void* r = tlb ? (void*)(tlb + 512 * li) : nullptr; ++li; return r; };
   if ((rc = b2l_ring_advance(d->input_pos, 1, d->ring_start, d->S, stream))) return rc;
   if ((rc = b2l_embedding(d->idx, d->idx_is_i64, d->wte, d->x, B, C, d->vocab, stream))) return rc;
   for (int l = 0; l < d->n_layer; ++l) {

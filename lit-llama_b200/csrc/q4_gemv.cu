@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
           for (int h = 0; h < halves; ++h)
             tma_bulk_g2s(sbase + L.ring + slot * STAGE_BYTES + h * HALF_STAGE_BYTES,
                          src + ((size_t)h * n_kb + (size_t)s * KBP_PER_STAGE) * KB_BYTES, bytes, bar_full + slot * 8);
+          if (p.tl != nullptr && blockIdx.x == 0 && it < 12) p.tl[40 + it] = globaltimer_ns();
           if (++slot == p.nst) { slot = 0; phase ^= 1; }
           if (it + 1 == min(total_stages, p.nst)) pdl_launch_dependents();  // ring full: next kernel may prefetch
         }
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
     uint32_t phase = 0;
     float* scratch = reinterpret_cast<float*>(smem + L.scratch);
     const uint8_t* xf_lane = smem + L.xf + t4 * 32;
+    int dbg_it = 0;
     for (int u = 0; u < n_units; ++u) {
       const int halves = min(2, rb_hi - (rb_lo + 2 * u));
       float acc[MAX_HALVES][2][4];
@@ -299,6 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
       for (int s = 0; s < stages_per_unit; ++s) {
         const int nkb = min(KBP_PER_STAGE, n_kb - s * KBP_PER_STAGE);
         mbar_wait(bar_full + slot * 8, phase);
+        if (p.tl != nullptr && blockIdx.x == 0 && tid == 0 && dbg_it < 12) p.tl[8 + 2 * dbg_it] = globaltimer_ns();
         const uint8_t* st_base = smem + L.ring + slot * STAGE_BYTES + lane * 16;
 #pragma unroll
         for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
@@ -327,6 +330,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + slot * 8);
+        if (p.tl != nullptr && blockIdx.x == 0 && tid == 0 && dbg_it < 12) p.tl[9 + 2 * dbg_it] = globaltimer_ns();
+        ++dbg_it;
         if (++slot == p.nst) { slot = 0; phase ^= 1; }
       }
       // column 0 of each 16x8 result: lanes with t == 0 hold rows g (acc[.][0]) and g + 8 (acc[.][2])

@@ -596,7 +596,7 @@ def sec_timeline():
                 model(tok, S, torch.tensor([pos0 + i], device=dev))
             st = model._decode
             n = 5 * model.config.n_layer + 1
-            tl = torch.zeros((n, 8), dtype=torch.int64, device=dev)
+            tl = torch.zeros((n, 64), dtype=torch.int64, device=dev)
             tl[:, 0] = 2**62
             st.args.timeline = tl.data_ptr()
             model(tok, S, torch.tensor([pos0 + 3], device=dev))
@@ -610,6 +610,11 @@ def sec_timeline():
             for li in range(5 * 4, 5 * 6 + 1):
                 r = [int(v) - base if int(v) not in (0, 2**62) else None for v in t[li, :7]]
                 print(f"  L{li // 5} {names[li % 5]:9s} {r}")
+            for li in (20, 23):  # layer 4 c_attn and fc12: CTA 0 per-stage stamps
+                b0 = int(t[li, 0])
+                st = [(int(t[li, 8 + 2 * i]) - b0, int(t[li, 9 + 2 * i]) - b0) for i in range(12) if int(t[li, 8 + 2 * i])]
+                pi = [int(t[li, 40 + i]) - b0 for i in range(12) if int(t[li, 40 + i])]
+                print(f"  {names[li % 5]} CTA0: wait_done={(int(t[li, 1]) - b0)} x_ready={(int(t[li, 2]) - b0)} stages(full_seen, done)={st} tma_issue={pi}")
             tot = int(t[n - 1, 4]) - int(t[0, 0])
             print(f"  whole step (first start -> lm_head end): {tot / 1e3:.1f} us; layer 4 start -> layer 5 start: "
                   f"{(int(t[25, 0]) - int(t[20, 0])) / 1e3:.2f} us")

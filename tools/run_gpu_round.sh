@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -25
+timeout 300 python tools/diag.py timeline 2>&1 | grep -E "CTA0|whole" | head -3
