@@ -220,7 +220,7 @@ def time_q4_launches(model, dev):
     def mk(w, x, ldx, y, ldy, pro, ns, epi, res):
         return L.Q4LinearArgs(x=x, ldx=ldx, qw_tiled=w.qw_mma if gemv else w.qw_tiled, scales=w.scales, zeros=w.zeros, sz_dtype=a.sz_dtype, y=y, ldy=ldy,
                               M=1, N=w.N, K=w.K, prologue=pro, norm_scale=ns, eps=a.eps, epilogue=epi, res=res, ldres=ldy,
-                              split_k=0, flags=0)
+                              split_k=0, flags=1)  # PDL, as b2l_decode_step launches them
 
     Cd = a.n_embd
     for i in range(a.n_layer):
@@ -368,6 +368,11 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         ach = W / t_q4 / 1e9
+        traffic = None
+        try:  # dram bytes of the kernel's launches of one token, from the committed ncu capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["bytes_per_token"]
+        except (OSError, KeyError, ValueError):
+            pass
         from lit_llama_b200 import _lib as L
         import ctypes as C
         launches = L.lib().b2l_decode_step_launches(C.byref(model._decode.args))
@@ -382,7 +387,7 @@ def main():
             "clocks": clk,
             "e2e": {"value": aggregate_throughput(world, Ke, t_e2e), "unit": "tokens/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 8, "steps": Ke},
             "gpu_launches": launches * K,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "kernel": q4_name, "launches_per_token": n_q4, "bytes_per_token_launches": W,
                          "peak_source": which,
                          "whole_token": {"bytes": bytes_per_token, "achieved": bytes_per_token * K / t_dev / 1e9,

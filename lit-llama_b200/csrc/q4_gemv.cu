@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
       sx = warp_sum(sx);
       if (lane == 0) red[8 + warp] = sx;   // the epilogue warp adds the 8 partials in a fixed order
       named_bar_sync(3, NT + 32);          // releases the epilogue warp too: xf and the partial sums are ready
-      if (tid == 0) tl_max(p.tl, 2);
+      if (tid == 0) { tl_max(p.tl, 2); if (p.tl != nullptr) atomicMin(p.tl + 60, globaltimer_ns()); }
     }
 
     // ---- weights: stage -> registers -> mma.sync.  Warp w takes k-block positions w and w + 8 of a stage
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
       __syncwarp();
       named_bar_arrive(6 + buf, NCW * 32 + 32);  // partials of this unit are in the scratch buffer
     }
-    if (tid == 0) tl_max(p.tl, 3);
+    if (tid == 0) { tl_max(p.tl, 3); if (p.tl != nullptr) atomicMin(p.tl + 61, globaltimer_ns()); }
   } else {
     // ===================== epilogue warp: lane = row of the 32-row unit =====================
     pdl_wait();

@@ -598,6 +598,8 @@ def sec_timeline():
             n = 5 * model.config.n_layer + 1
             tl = torch.zeros((n, 64), dtype=torch.int64, device=dev)
             tl[:, 0] = 2**62
+            tl[:, 60] = 2**62
+            tl[:, 61] = 2**62
             st.args.timeline = tl.data_ptr()
             model(tok, S, torch.tensor([pos0 + 3], device=dev))
             torch.cuda.synchronize()
@@ -609,7 +611,10 @@ def sec_timeline():
                   "start(min) | wait_done(max) | x_ready(max) | loop_done(max) | end(max) | x_loaded(tid0) | after_ss_bar(tid0)")
             for li in range(5 * 4, 5 * 6 + 1):
                 r = [int(v) - base if int(v) not in (0, 2**62) else None for v in t[li, :7]]
-                print(f"  L{li // 5} {names[li % 5]:9s} {r}")
+                extra = ""
+                if li % 5 != 1:
+                    extra = f"  | x_ready min..max {int(t[li, 60]) - base}..{r[2]}  loop_done min..max {int(t[li, 61]) - base}..{r[3]}"
+                print(f"  L{li // 5} {names[li % 5]:9s} {r}{extra}")
             for li in (20, 23):  # layer 4 c_attn and fc12: CTA 0 per-stage stamps
                 b0 = int(t[li, 0])
                 st = [(int(t[li, 8 + 2 * i]) - b0, int(t[li, 9 + 2 * i]) - b0) for i in range(12) if int(t[li, 8 + 2 * i])]
