@@ -1,0 +1,198 @@
+"""Tensor-parallel decode across GPUs of one node (new capability - the
+reference has no multi-GPU inference, every script is `L.Fabric(devices=1)`).
+
+Megatron-style sharding of the reference Block (split dims as recorded by the reference's own
+checkpoint converter, scripts/convert_checkpoint.py:56-64):
+
+  c_attn    (3C, C)   column-parallel BY HEADS inside each of q, k, v   -> local [q_r; k_r; v_r]
+  attention           local heads, local KV cache
+  attn.c_proj (C, C)  row-parallel over `in` (the local heads' slice)   -> all-reduce(sum)
+  c_fc1/c_fc2         column-parallel
+  mlp.c_proj          row-parallel                                       -> all-reduce(sum)
+  lm_head   (V, C)    column-parallel + all-gather of the logits
+  wte, RMSNorm scales replicated
+
+Two all-reduces per Block are needed for exact semantics (rms_2 needs the full post-attention
+residual, model.py:165-167).  One process per GPU, `torch.distributed` (NCCL over NVLink) for the
+exchange; every local op is the same kernel the single-GPU path uses (include/b2l.h).  Row-parallel
+int4 linears keep their per-row scale/zero on every rank: `y = s*(sum_k lv*x - z*sum_k x)` is linear in
+the K slice, so each rank's kernel uses its LOCAL sum(x) and the partial results simply add.
+
+The per-rank partial products are rounded to bf16 before the reduction (the kernels' output
+dtype), so a TP result can differ from the single-GPU one by one bf16 ulp per reduction.
+"""
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib as L
+from .model import LLaMAConfig, RMSNorm, _add, build_rope_cache
+from .quantization import ColBlockQuantizedLinear
+
+
+# ----------------------------------------------------------------------------- sharding (host logic, any device)
+def _rows(t: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    return t.index_select(0, idx.to(t.device))
+
+
+def shard_linear(sd: Dict[str, torch.Tensor], prefix: str, *, rows: Optional[torch.Tensor] = None,
+                 k_range: Optional[Tuple[int, int]] = None) -> Dict[str, torch.Tensor]:
+    """One linear of a reference-format gptq.int4 state dict, restricted to output `rows`
+    (column-parallel) or to the input range `k_range` (row-parallel).  Packed weights keep
+    the reference layout (uint8 (out, in/2), strides (1, out))."""
+    qw, sc, z = sd[prefix + ".quant_weight"], sd[prefix + ".scales"], sd[prefix + ".zeros"]
+    if sc.shape[1] != 1:
+        raise RuntimeError("tensor parallelism supports one (scale, zero) per output row (gptq.int4 as produced by --quantize gptq.int4)")
+    if rows is not None:
+        qw, sc, z = _rows(qw, rows), _rows(sc, rows), _rows(z, rows)
+    if k_range is not None:
+        k0, k1 = k_range
+        assert k0 % 2 == 0 and k1 % 2 == 0
+        qw = qw[:, k0 // 2 : k1 // 2]
+    return {prefix + ".quant_weight": qw.t().contiguous().t(), prefix + ".scales": sc.contiguous(), prefix + ".zeros": z.contiguous()}
+
+
+def shard_state_dict(sd: Dict[str, torch.Tensor], rank: int, world: int, n_head: int) -> Dict[str, torch.Tensor]:
+    """The slice of a full gptq.int4 checkpoint that rank `rank` of `world` holds."""
+    C = sd["transformer.wte.weight"].shape[1]
+    V = sd["lm_head.scales"].shape[0]
+    assert n_head % world == 0 and V % world == 0, "n_head and the padded vocabulary must divide by the TP degree"
+    hs = C // n_head
+    nh_l = n_head // world
+    heads = torch.arange(rank * nh_l, (rank + 1) * nh_l)
+    head_rows = (heads.unsqueeze(1) * hs + torch.arange(hs).unsqueeze(0)).reshape(-1)  # rows of one of q/k/v for the local heads
+    qkv_rows = torch.cat([head_rows, C + head_rows, 2 * C + head_rows])
+    out: Dict[str, torch.Tensor] = {}
+    n_layer = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.h."))
+    for i in range(n_layer):
+        p = f"transformer.h.{i}."
+        nh = sd[p + "mlp.c_fc1.scales"].shape[0]
+        assert nh % world == 0
+        f_rows = torch.arange(rank * (nh // world), (rank + 1) * (nh // world))
+        out.update(shard_linear(sd, p + "attn.c_attn", rows=qkv_rows))
+        out.update(shard_linear(sd, p + "attn.c_proj", k_range=(rank * nh_l * hs, (rank + 1) * nh_l * hs)))
+        out.update(shard_linear(sd, p + "mlp.c_fc1", rows=f_rows))
+        out.update(shard_linear(sd, p + "mlp.c_fc2", rows=f_rows))
+        out.update(shard_linear(sd, p + "mlp.c_proj", k_range=(rank * (nh // world), (rank + 1) * (nh // world))))
+        out[p + "rms_1.scale"] = sd[p + "rms_1.scale"]
+        out[p + "rms_2.scale"] = sd[p + "rms_2.scale"]
+    out.update(shard_linear(sd, "lm_head", rows=torch.arange(rank * (V // world), (rank + 1) * (V // world))))
+    out["transformer.wte.weight"] = sd["transformer.wte.weight"]
+    out["transformer.ln_f.scale"] = sd["transformer.ln_f.scale"]
+    return out
+
+
+# ----------------------------------------------------------------------------- the sharded model
+def _q4(in_f: int, out_f: int) -> ColBlockQuantizedLinear:
+    return ColBlockQuantizedLinear(in_f, out_f, False, bits=4, tile_cols=-1)
+
+
+class _TPAttention(nn.Module):
+    def __init__(self, C: int, C_l: int) -> None:
+        super().__init__()
+        self.c_attn = _q4(C, 3 * C_l)
+        self.c_proj = _q4(C_l, C)
+
+
+class _TPMLP(nn.Module):
+    def __init__(self, C: int, nh_l: int) -> None:
+        super().__init__()
+        self.c_fc1 = _q4(C, nh_l)
+        self.c_fc2 = _q4(C, nh_l)
+        self.c_proj = _q4(nh_l, C)
+
+
+class _TPBlock(nn.Module):
+    def __init__(self, C: int, C_l: int, nh_l: int) -> None:
+        super().__init__()
+        self.rms_1 = RMSNorm(C)
+        self.attn = _TPAttention(C, C_l)
+        self.rms_2 = RMSNorm(C)
+        self.mlp = _TPMLP(C, nh_l)
+
+
+class TPLLaMA(nn.Module):
+    """LLaMA.forward (model.py:76-122) with every quantized linear sharded over `group`.
+    State-dict keys equal the reference's, so `load_state_dict(shard_state_dict(full, rank, world, n_head))` works."""
+
+    def __init__(self, config: LLaMAConfig, rank: int, world: int, n_hidden: int, group=None) -> None:
+        super().__init__()
+        assert config.n_head % world == 0 and n_hidden % world == 0 and config.padded_vocab_size % world == 0
+        self.config, self.rank, self.world, self.group = config, rank, world, group
+        C = config.n_embd
+        self.hs = C // config.n_head
+        self.nh_l = config.n_head // world
+        C_l = self.nh_l * self.hs
+        self.lm_head = _q4(C, config.padded_vocab_size // world)
+        self.transformer = nn.ModuleDict(dict(
+            wte=nn.Embedding(config.padded_vocab_size, C),
+            h=nn.ModuleList(_TPBlock(C, C_l, n_hidden // world) for _ in range(config.n_layer)),
+            ln_f=RMSNorm(C),
+        ))
+        self.rope_cache: Optional[torch.Tensor] = None
+        self.kv_caches: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        self._ring: Optional[torch.Tensor] = None
+        self._work: Optional[torch.Tensor] = None
+
+    def reset_cache(self) -> None:
+        self.kv_caches.clear()
+        if self._ring is not None:
+            self._ring.zero_()
+
+    def _all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    @torch.no_grad()
+    def forward(self, idx: torch.Tensor, max_seq_length: Optional[int] = None, input_pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, T = idx.shape
+        if not idx.is_cuda:
+            raise RuntimeError("TPLLaMA.forward: CUDA only (no CPU fallback)")
+        if input_pos is None:
+            raise RuntimeError("TPLLaMA implements the KV-cache path (input_pos given), which is what generate() uses")
+        cfg, dev, lib = self.config, idx.device, L.lib()
+        S = cfg.block_size if max_seq_length is None else max_seq_length
+        C, hs, nh_l = cfg.n_embd, self.hs, self.nh_l
+        if self.rope_cache is None:
+            self.rope_cache = build_rope_cache(cfg.block_size, hs, idx.dtype, dev).float().contiguous()
+        if self._ring is None:
+            self._ring = torch.zeros(1, dtype=torch.int32, device=dev)
+        if not self.kv_caches:
+            shape = (B, nh_l, S, hs)
+            self.kv_caches = [(torch.zeros(shape, device=dev, dtype=torch.bfloat16), torch.zeros(shape, device=dev, dtype=torch.bfloat16))
+                              for _ in range(cfg.n_layer)]
+            self._work = torch.zeros(lib.b2l_attn_workspace_bytes(B, nh_l, hs, T, S) // 4 + 1, device=dev, dtype=torch.float32)
+        if self._work.numel() * 4 < lib.b2l_attn_workspace_bytes(B, nh_l, hs, T, S):
+            self._work = torch.zeros(lib.b2l_attn_workspace_bytes(B, nh_l, hs, T, S) // 4 + 1, device=dev, dtype=torch.float32)
+        pos = input_pos.reshape(-1).to(torch.int64)
+        wte = self.transformer.wte.weight
+        if wte.dtype != torch.bfloat16:
+            raise RuntimeError("TPLLaMA: the model must be bf16")
+        idx_c = idx.contiguous() if idx.dtype in (torch.int32, torch.int64) else idx.to(torch.int64).contiguous()
+        x = torch.empty((B, T, C), device=dev, dtype=torch.bfloat16)
+        L.check(lib.b2l_embedding(idx_c.data_ptr(), 1 if idx_c.dtype == torch.int64 else 0, wte.data_ptr(), x.data_ptr(), B * T, C,
+                                  wte.shape[0], L.stream_ptr()), "b2l_embedding")
+        L.check(lib.b2l_ring_advance(pos.data_ptr(), T, self._ring.data_ptr(), S, L.stream_ptr()), "b2l_ring_advance")
+        for i, blk in enumerate(self.transformer.h):
+            qkv = blk.attn.c_attn(blk.rms_1(x)).contiguous()               # (B, T, 3*C_l): local heads of q | k | v
+            k_c, v_c = self.kv_caches[i]
+            y = torch.empty((B, T, nh_l * hs), device=dev, dtype=torch.bfloat16)
+            rc = lib.b2l_attention(qkv.data_ptr(), k_c.data_ptr(), v_c.data_ptr(), self.rope_cache.data_ptr(), pos.data_ptr(),
+                                   self._ring.data_ptr(), y.data_ptr(), self._work.data_ptr(), B, T, nh_l, hs, S, cfg.block_size, 0,
+                                   L.stream_ptr())
+            L.check(rc, "b2l_attention")
+            x = _add(x, self._all_reduce(blk.attn.c_proj(y)))              # row-parallel partials -> sum  (model.py:166)
+            h = blk.rms_2(x)
+            a, b = blk.mlp.c_fc1(h).contiguous(), blk.mlp.c_fc2(h).contiguous()
+            g = torch.empty_like(a)
+            L.check(lib.b2l_silu_mul(a.data_ptr(), b.data_ptr(), g.data_ptr(), a.numel(), L.stream_ptr()), "b2l_silu_mul")
+            x = _add(x, self._all_reduce(blk.mlp.c_proj(g)))               # (model.py:167)
+        logits_l = self.lm_head(self.transformer.ln_f(x)).contiguous()     # (B, T, V / world)
+        if self.world == 1:
+            return logits_l
+        parts = [torch.empty_like(logits_l) for _ in range(self.world)]
+        dist.all_gather(parts, logits_l, group=self.group)
+        return torch.cat(parts, dim=-1)
