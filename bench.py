@@ -140,8 +140,14 @@ def cpu_baseline(n_blocks=4, threads=None):
 
     from oracle import llama_oracle as O
 
-    if threads:
-        torch.set_num_threads(threads)
+    if threads is None:
+        # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1, which would
+        # silently turn the baseline into a single-core run)
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     c = O.CONFIGS[MODEL]
     C, nhd, L = c["n_embd"], c["n_head"], c["n_layer"]
     nh = O.n_hidden_for(C)

@@ -95,7 +95,10 @@ def main():
     dt = (time.perf_counter() - t0) / 32
     if rank == 0:
         print(f"[tp={world}] 7B decode, eager module path: {dt * 1e6:.0f} us/token  {1 / dt:.1f} tok/s", flush=True)
-    # CUDA graph of one step (NCCL collectives captured)
+    # CUDA graph of one step (NCCL collectives captured) - opt-in: B2L_TP_GRAPH=1
+    if os.environ.get("B2L_TP_GRAPH") != "1":
+        dist.destroy_process_group()
+        return
     try:
         st_tok, st_pos = tok.clone(), pos[36].clone()
         s = torch.cuda.Stream()
