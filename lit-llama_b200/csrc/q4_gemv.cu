@@ -137,6 +137,9 @@ __device__ __forceinline__ uint32_t lop_and_or(uint32_t a, uint32_t mask, uint32
   return d;
 }
 
+// MAXC = activation chunks (2048 elements each) a thread block caches in registers during the prologue:
+// 6 covers K <= 12288 (every 7B/13B/30B layer), 12 covers K <= 24576 (65B mlp.c_proj, K = 22016).
+template <int MAXC>
 __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const SmemLayout L = smem_layout(p.nst, p.K);
@@ -193,7 +196,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
     {
       const bool norm = (p.prologue == B2L_PRO_RMSNORM);
       constexpr int NT = NCW * 32;   // 256 threads, 8 elements each per pass
-      constexpr int MAXC = 6;        // up to 12288 elements in registers
       uint4 xv[MAXC], gv[MAXC];
       // the RMSNorm scale is a weight: fetch it BEFORE waiting for the producing kernel (it comes from HBM,
       // behind the queued weight prefetch; after the wait it would sit on the critical path)
@@ -472,7 +474,7 @@ extern "C" int b2l_q4_gemv(const b2l_q4_linear_args* a, b2l_stream_t stream) {
   B2L_CHECK_ARG(a != nullptr, "b2l_q4_gemv: null args");
   B2L_CHECK_ARG(a->x && a->qw_tiled && a->scales && a->zeros && a->y, "b2l_q4_gemv: null pointer");
   B2L_CHECK_SUPPORTED(a->M == 1, "b2l_q4_gemv: M=%d (this kernel is the batch-1 path; use b2l_q4_linear_tc)", a->M);
-  B2L_CHECK_SUPPORTED(a->K > 0 && a->K % KB == 0 && a->K <= 6 * NCW * 32 * 8, "b2l_q4_gemv: K=%d must be a multiple of %d and <= %d", a->K, KB, 6 * NCW * 32 * 8);
+  B2L_CHECK_SUPPORTED(a->K > 0 && a->K % KB == 0 && a->K <= 12 * NCW * 32 * 8, "b2l_q4_gemv: K=%d must be a multiple of %d and <= %d", a->K, KB, 12 * NCW * 32 * 8);
   B2L_CHECK_ARG(a->N > 0, "b2l_q4_gemv: bad N");
   B2L_CHECK_ARG(((uintptr_t)a->x % 16 == 0) && ((uintptr_t)a->qw_tiled % 16 == 0), "b2l_q4_gemv: x / qw_tiled must be 16-byte aligned");
   B2L_CHECK_ARG(a->sz_dtype == B2L_BF16 || a->sz_dtype == B2L_F32, "b2l_q4_gemv: bad sz_dtype");
@@ -506,14 +508,17 @@ extern "C" int b2l_q4_gemv(const b2l_q4_linear_args* a, b2l_stream_t stream) {
   if (nst < 2) nst = 2;
   p.nst = nst;
   const SmemLayout L = smem_layout(nst, a->K);
-  static size_t configured_smem = 0;
-  if (L.total > configured_smem) {
-    B2L_CUDA(cudaFuncSetAttribute(q4_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    configured_smem = L.total;
+  const bool wide = a->K > 6 * NCW * 32 * 8;
+  static size_t configured_smem[2] = {0, 0};
+  if (L.total > configured_smem[wide]) {
+    if (wide) B2L_CUDA(cudaFuncSetAttribute(q4_gemv_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    else B2L_CUDA(cudaFuncSetAttribute(q4_gemv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    configured_smem[wide] = L.total;
   }
   int grid = a->split_k > 0 ? a->split_k : (env_cps > 0 ? env_cps : 2) * sm_count();  // split_k doubles as a grid override
   if (grid > p.n_rb) grid = p.n_rb;
   LaunchCfg lc(dim3(grid), dim3(NTHREADS), L.total, (cudaStream_t)stream, (a->flags & B2L_F_PDL) != 0, 1);
-  B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, q4_gemv_kernel, p));
+  if (wide) B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, q4_gemv_kernel<12>, p));
+  else B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, q4_gemv_kernel<6>, p));
   return 0;
 }

@@ -318,6 +318,7 @@ class LLaMA(nn.Module):
         self._ring: Optional[torch.Tensor] = None
         self._kv_store: Optional[torch.Tensor] = None
         self._decode: Optional[_DecodeState] = None
+        self._module_graph = None  # CUDA graph of the module-by-module decode step (non-fused Linear kinds)
         self._fast_ok: Optional[bool] = None  # every Linear is a tcgen05-capable int4 layer (checked once)
         self._fc12_cache = {}
 
@@ -347,6 +348,7 @@ class LLaMA(nn.Module):
         self.kv_caches.clear()
         self._kv_store = None
         self._decode = None
+        self._module_graph = None
         if self._ring is not None:
             self._ring.zero_()
 
@@ -441,6 +443,7 @@ class LLaMA(nn.Module):
             self._kv_store = torch.zeros((cfg.n_layer, 2, B, cfg.n_head, max_seq_length, hs), device=idx.device, dtype=torch.bfloat16)
             self.kv_caches = [(self._kv_store[i, 0], self._kv_store[i, 1]) for i in range(cfg.n_layer)]
             self._decode = None
+            self._module_graph = None
 
         # ---- decode: one C call per token, replayed as a CUDA graph
         st = None
@@ -466,7 +469,32 @@ class LLaMA(nn.Module):
             st.calls += 1
             return st.logits.clone() if self.copy_logits else st.logits
 
-        # ---- prefill / no-cache / non-int4 linears: module by module
+        # ---- single-token decode with any other Linear kind (llm.int8, gptq.int8, grouped scales, dense):
+        #      the module-by-module launch sequence, replayed as a CUDA graph once warm
+        if input_pos is not None and T == 1 and self.graph_after and idx.dtype in (torch.int32, torch.int64):
+            key = (B, max_seq_length, idx.dtype)
+            mg = self._module_graph
+            if mg is None or mg["key"] != key:
+                mg = self._module_graph = dict(key=key, calls=0, graph=None, idx=torch.zeros((B, 1), dtype=idx.dtype, device=idx.device),
+                                               pos=torch.zeros(1, dtype=torch.int64, device=idx.device), out=None)
+            mg["idx"].copy_(idx)
+            mg["pos"].copy_(input_pos.reshape(-1)[-1:])
+            if mg["graph"] is not None:
+                mg["graph"].replay()
+                return mg["out"].clone() if self.copy_logits else mg["out"]
+            mg["calls"] += 1
+            if mg["calls"] > self.graph_after:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    mg["out"] = self._forward_modules(mg["idx"], max_seq_length, mg["pos"])
+                mg["graph"] = g
+                g.replay()
+                return mg["out"].clone() if self.copy_logits else mg["out"]
+        return self._forward_modules(idx, max_seq_length, input_pos)
+
+    def _forward_modules(self, idx: torch.Tensor, max_seq_length: int, input_pos: Optional[torch.Tensor]) -> torch.Tensor:
+        """Prefill, no-cache forward and non-fused decode: one kernel (or two) per reference module."""
+        B, T = idx.size()
         x = torch.empty((B, T, self.config.n_embd), device=idx.device, dtype=torch.bfloat16)
         wte = self.transformer.wte.weight
         if wte.dtype != torch.bfloat16:

@@ -120,7 +120,7 @@ class ColBlockQuantizedLinear(torch.nn.Module):
 
     @property
     def gemv_capable(self) -> bool:
-        return self.tc_capable and self.in_features % 64 == 0 and self.in_features <= 12288
+        return self.tc_capable and self.in_features % 64 == 0 and self.in_features <= 24576
 
     def forward(self, inp):
         L.require_cuda_bf16(inp, "ColBlockQuantizedLinear.forward")

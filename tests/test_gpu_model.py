@@ -248,9 +248,10 @@ def test_llm_int8_model_vs_oracle(dev):
     with torch.no_grad():
         got = [model(prompt.to(dev), 16, torch.arange(5, device=dev))]
         want = [oracle.forward(prompt, 16, torch.arange(5))]
-        for i, t in enumerate([9, 60]):
+        for i, t in enumerate([9, 60, 3, 77, 12, 45]):  # > graph_after steps: the later ones are CUDA-graph replays
             got.append(model(torch.tensor([[t]], device=dev), 16, torch.tensor([5 + i], device=dev)))
             want.append(oracle.forward(torch.tensor([[t]]), 16, torch.tensor([5 + i])))
+    assert model._module_graph is not None and model._module_graph["graph"] is not None
     for a, b in zip(got, want):
         a, b = a.float().cpu(), b.float()
         assert (a - b).norm() / b.norm() < 2e-2, float((a - b).norm() / b.norm())

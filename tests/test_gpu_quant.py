@@ -142,6 +142,26 @@ def test_gemv_prologue_epilogue_and_determinism(dev):
         assert torch.equal(y0, y1)
 
 
+@pytest.mark.parametrize("name,N,K", [("13B c_attn", 15360, 5120), ("13B mlp_proj", 5120, 13824), ("65B c_proj", 8192, 8192),
+                                      ("65B mlp_proj", 8192, 22016)])
+def test_gemv_13b_65b_shapes(dev, name, N, K):
+    """The other BASELINE model widths through the batch-1 kernel (K = 22016 exercises the wide-row prologue)."""
+    from gpu_util import gemv_call, rand_q4, ref_linear, relerr, tile_mma
+    from lit_llama_b200 import _lib as L
+
+    lv, qw, sc, z = rand_q4(N, K, dev, seed=N % 97 + K)
+    qt = tile_mma(L, qw, N, K)
+    x = torch.randn(1, K, device=dev).bfloat16()
+    g = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
+    y, err = gemv_call(L, x, qt, sc, z, N, K)
+    assert err is None, err
+    assert relerr(y, ref_linear(x, lv, sc, z)) < 1e-3 + 2.0 ** -9
+    xn = g * (x * torch.rsqrt(torch.mean(x * x, dim=-1, keepdim=True) + 1e-5))
+    y, err = gemv_call(L, x, qt, sc, z, N, K, prologue=1, norm_scale=g)
+    assert err is None, err
+    assert relerr(y, ref_linear(xn, lv, sc, z)) < 1e-3 + 2.0 ** -9
+
+
 @pytest.mark.parametrize("name,N,K", [("c_attn", 12288, 4096), ("c_proj", 4096, 4096), ("c_fc12", 22016, 4096),
                                       ("mlp_proj", 4096, 11008), ("lm_head", 32000, 4096)])
 def test_tc_linear_7b_shapes(dev, name, N, K):

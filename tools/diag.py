@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "trace", "bench_layers", "bench_gemv", "bench_step", "timeline"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_step_int8", "timeline"]
 
 
 def rand_q4(N, K, dev, seed=0, sz_dtype=None, groups=1, bits=4):
@@ -573,6 +573,43 @@ def sec_bench_step():
                 torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / 60 * 1e3
             print(f"decode step 7B pos~16-80 pdl={pdl} graph={graph_after > 0}: {us:.1f} us/token  {1e6 / us:.1f} tok/s")
+
+
+def sec_bench_step_int8():
+    """LLaMA-7B --quantize llm.int8 decode (BASELINE config 2): module path replayed as a CUDA graph."""
+    import torch
+    import lit_llama_b200 as P
+    from lit_llama_b200.utils import quantization
+
+    dev = torch.device("cuda")
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(dev), quantization("llm.int8"):
+            model = P.LLaMA.from_name("7B")
+    finally:
+        torch.set_default_dtype(prev)
+    model.eval()
+    S = 2048
+    model.copy_logits = False
+    idx = torch.randint(0, 32000, (1, 16), device=dev, dtype=torch.int32)
+    with torch.no_grad():
+        model(idx, S, torch.arange(16, device=dev))
+        tok = torch.randint(0, 32000, (1, 1), device=dev, dtype=torch.int32)
+        pos = [torch.tensor([16 + i], device=dev) for i in range(72)]
+        for i in range(6):
+            model(tok, S, pos[i])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(6, 70):
+            model(tok, S, pos[i])
+        e1.record()
+        torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 64 * 1e3
+    W8 = 6.6132e9
+    print(f"decode step 7B llm.int8 pos~16-90 graph={model._module_graph['graph'] is not None}: {us:.1f} us/token  {1e6 / us:.1f} tok/s  "
+          f"({W8 / us / 1e3:.0f} GB/s of weights = {W8 / us / 1e3 / 6573.2:.3f} of measured HBM peak)")
 
 
 def sec_timeline():
