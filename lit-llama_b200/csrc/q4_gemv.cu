@@ -17,12 +17,18 @@
 // Work split: a persistent CTA owns 16-row blocks rb = cta, cta + grid, ... over the FULL K
 // (so nothing is reduced across CTAs and the result is deterministic).  The 8 consumer warps
 // split K inside a stage; their fp32 partials meet in shared memory, where the epilogue warp
-// applies y = scale * (acc - (128 + zero) * sum(x)) and the fused epilogue.
+// applies y = scale * (acc - (1024 + zero) * sum_lo(x) - (64 + zero) * sum_hi(x)) and the fused epilogue.
 //
 // Weight layout (b2l_q4_tile_mma): [N/16 row blocks][K/64 k blocks][32 lanes][16 B].  Word c of
 // lane (g = lane/4, t = lane%4) holds the A fragment of k16 chunk c: nibble s (s < 4) is row
-// g + 8*(s&1), k = 64*kb + 16*c + 2*t + 8*(s>>1); nibble s+4 is the same row at k+1.  So
-// ((w >> 4s) & 0x000f000f) | 0x43004300 is register a_s of mma.m16n8k16 as bf16 (128 + level).
+// g + 8*(s>>1), k = 64*kb + 16*c + 2*t + 8*(s&1); nibble s+4 is the same row at k+1.  The A
+// registers of mma.m16n8k16 are built as fp16 pairs with one shift per word:
+//   a0 = (w      & 0x000f000f) | 0x64006400   = 1024 + level       (row g,   k lower half)
+//   a2 = (w      & 0x00f000f0) | 0x64006400   = 1024 + 16 * level  (row g,   k upper half)
+//   a1, a3 = the same two masks on w >> 8                          (row g+8)
+// and the activations of the upper half are fed as x / 16 (exact in fp16), so the accumulator holds
+// sum(level * x) + 1024 * sum_lo(x) + 64 * sum_hi(x); the two sums are removed with the zero point.
+// bf16 -> fp16 of the activations is exact inside the fp16 normal range; |x| > 65504 saturates.
 #include <cstdlib>
 
 #include "b2l_common.cuh"
@@ -106,9 +112,9 @@ __device__ __forceinline__ void named_bar_arrive(int id, int n) {
   }
 }
 
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -123,17 +129,23 @@ __host__ __device__ inline SmemLayout smem_layout(int nst, int K) {
   L.ring = o;    o += (uint32_t)nst * STAGE_BYTES;
   L.xf = o;      o += (uint32_t)(K / KB) * 128;       // B fragments: [k block][t (4)][32 B]
   L.scratch = o; o += 2 * NCW * RB * MAX_HALVES * 4;  // [buf][warp][half][row] fp32 partials
-  L.red = o;     o += 64;                             // per-warp reduction scratch + sum(x)
+  L.red = o;     o += 128;                            // per-warp reduction scratch: sum of squares, sum(x) of either k class
   o = (o + 7u) & ~7u;
   L.bars = o;    o += 2 * MAX_STAGES * 8;
   L.total = (o + 127u) & ~127u;
   return L;
 }
 
-// (w >> shift) & 0x000f000f | 0x43004300 in one LOP3: mask and magic live in registers
+// (w & mask) | magic in one LOP3: masks and magic live in registers
 __device__ __forceinline__ uint32_t lop_and_or(uint32_t a, uint32_t mask, uint32_t magic) {
   uint32_t d;
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));
+  return d;
+}
+// two fp32 -> packed fp16 (lo in bits 0..15), saturating: an activation beyond +-65504 clamps instead of becoming inf
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
 
@@ -264,18 +276,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
               w[q] = *reinterpret_cast<const uint32_t*>(&y2);
             }
           }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) sx += __uint_as_float(w[q] << 16) + __uint_as_float(w[q] & 0xffff0000u);
           // 8 consecutive k = half of a k16 chunk: pair q (k = k0 + 2q, +1) is B register (half) of lane t = q
-          // xf[k block][t][chunk c16 (4)][half (2)] u32
+          // xf[k block][t][chunk c16 (4)][half (2)] u32.  The half is (tid & 1): a thread only ever sees one k class.
+          // The tensor-core operand is fp16 (exact for a bf16 value in the fp16 range); the upper half of every
+          // k16 chunk is pre-divided by 16 because its weights are unpacked as 1024 + 16*level (see the main loop).
           const int kb = k >> 6, c16 = (k >> 4) & 3, half = (k >> 3) & 1;
+          const float pre = half ? 0.0625f : 1.0f;
           uint32_t* dst = reinterpret_cast<uint32_t*>(smem + L.xf + kb * 128);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q * 8 + c16 * 2 + half] = w[q];
+          for (int q = 0; q < 4; ++q) {
+            const float lo = __uint_as_float(w[q] << 16), hi = __uint_as_float(w[q] & 0xffff0000u);
+            sx += lo + hi;
+            dst[q * 8 + c16 * 2 + half] = pack_f16x2(lo * pre, hi * pre);
+          }
         }
       }
-      sx = warp_sum(sx);
-      if (lane == 0) red[8 + warp] = sx;   // the epilogue warp adds the 8 partials in a fixed order
+      // even lanes hold lower-half (k % 16 < 8) sums, odd lanes upper-half sums
+#pragma unroll
+      for (int o = 16; o > 1; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      if (lane < 2) red[8 + 8 * lane + warp] = sx;   // the epilogue warp adds the 8 partials of each class in a fixed order
       named_bar_sync(3, NT + 32);          // releases the epilogue warp too: xf and the partial sums are ready
       if (tid == 0) { tl_max(p.tl, 2); if (p.tl != nullptr) atomicMin(p.tl + 60, globaltimer_ns()); }
     }
@@ -283,9 +302,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
     // ---- weights: stage -> registers -> mma.sync.  Warp w takes k-block positions w and w + 8 of a stage
     // and, for each, both 16-row halves of the unit (the B fragments are loaded once per position).
     const int t4 = lane & 3;
-    uint32_t kmask, kmagic;
+    // fp16 unpack: (w & 0x000f000f) | 0x64006400 = (1024 + level) pairs, (w & 0x00f000f0) | 0x64006400 =
+    // (1024 + 16 * level) pairs -- two of the four A registers of a k16 chunk need no shift at all
+    uint32_t kmask, kmask4, kmagic;
     asm volatile("mov.b32 %0, 0x000f000f;" : "=r"(kmask));
-    asm volatile("mov.b32 %0, 0x43004300;" : "=r"(kmagic));
+    asm volatile("mov.b32 %0, 0x00f000f0;" : "=r"(kmask4));
+    asm volatile("mov.b32 %0, 0x64006400;" : "=r"(kmagic));
     int slot = 0;
     uint32_t phase = 0;
     float* scratch = reinterpret_cast<float*>(smem + L.scratch);
@@ -320,11 +342,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                   uint32_t a[4];
-                  a[0] = lop_and_or(ww[c], kmask, kmagic);
-                  a[1] = lop_and_or(ww[c] >> 4, kmask, kmagic);
-                  a[2] = lop_and_or(ww[c] >> 8, kmask, kmagic);
-                  a[3] = lop_and_or(ww[c] >> 12, kmask, kmagic);
-                  mma_bf16_16816(acc[h][c & 1], a, bb[2 * c], bb[2 * c + 1]);
+                  const uint32_t w8 = ww[c] >> 8;
+                  a[0] = lop_and_or(ww[c], kmask, kmagic);   // row g,     k 2t..2t+1     : 1024 + q
+                  a[1] = lop_and_or(w8, kmask, kmagic);      // row g + 8, k 2t..2t+1     : 1024 + q
+                  a[2] = lop_and_or(ww[c], kmask4, kmagic);  // row g,     k 2t+8..2t+9   : 1024 + 16 q  (x / 16 in B)
+                  a[3] = lop_and_or(w8, kmask4, kmagic);     // row g + 8, k 2t+8..2t+9   : 1024 + 16 q
+                  mma_f16_16816(acc[h][c & 1], a, bb[2 * c], bb[2 * c + 1]);
                 }
               }
             }
@@ -357,9 +380,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
     const float* red = reinterpret_cast<const float*>(smem + L.red);
     const float* scratch = reinterpret_cast<const float*>(smem + L.scratch);
     named_bar_sync(3, NCW * 32 + 32);
-    float sumx = 0.f;
+    // sum of the (normalised) activations over the lower (k % 16 < 8) and upper halves of the k16 chunks
+    float sum_lo = 0.f, sum_hi = 0.f;
 #pragma unroll
-    for (int w = 0; w < NCW; ++w) sumx += red[8 + w];  // sum over K of the (normalised) activations
+    for (int w = 0; w < NCW; ++w) { sum_lo += red[8 + w]; sum_hi += red[16 + w]; }
     // both scratch buffers start free
     if (n_units > 0) named_bar_arrive(4, NCW * 32 + 32);
     if (n_units > 1) named_bar_arrive(5, NCW * 32 + 32);
@@ -372,7 +396,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
       const int orow = (rb + half) * RB + row;             // row of the (interleaved) weight matrix
       const int o = min(orow, p.N - 1);
       const float sc = load_sz(p.scales, p.szdt, o);
-      const float zz = 128.0f + load_sz(p.zeros, p.szdt, o);
+      const float zero = load_sz(p.zeros, p.szdt, o);
       float resv = 0.f;
       if (p.epilogue == B2L_EPI_RESIDUAL && active && orow < p.N) resv = bf2f(p.res[orow]);
       named_bar_sync(6 + buf, NCW * 32 + 32);
@@ -380,7 +404,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
 #pragma unroll
       for (int w = 0; w < NCW; ++w) t += scratch[((buf * NCW + w) * MAX_HALVES + half) * RB + row];  // fixed order: deterministic
       if (u + 2 < n_units) named_bar_arrive(4 + buf, NCW * 32 + 32);                                   // scratch buffer free again
-      const float v = rbf(sc * (t - zz * sumx));
+      // t = sum q x + 1024 sum_lo + 64 sum_hi  (upper half: (1024 + 16 q) * x / 16)
+      const float v = rbf(sc * ((t - (1024.0f + zero) * sum_lo) - (64.0f + zero) * sum_hi));
       if (p.epilogue == B2L_EPI_SWIGLU) {
         // rows 0..7 of a 16-row block are c_fc1[o..o+7], rows 8..15 are c_fc2[o..o+7]
         const float b = __shfl_down_sync(0xffffffffu, v, 8);
@@ -411,8 +436,8 @@ __global__ void q4_tile_mma_kernel(const uint8_t* __restrict__ qw, uint32_t* __r
 #pragma unroll
   for (int s = 0; s < 8; ++s) {
     const int ss = s & 3;
-    const int row = rb * RB + g + 8 * (ss & 1);
-    const int k = kb * KB + 16 * c + 2 * t + 8 * (ss >> 1) + (s >> 2);
+    const int row = rb * RB + g + 8 * (ss >> 1);
+    const int k = kb * KB + 16 * c + 2 * t + 8 * (ss & 1) + (s >> 2);
     if (row < N) {
       const uint8_t b = qw[(size_t)(k >> 1) * N + row];
       w |= (uint32_t)((b >> ((k & 1) * 4)) & 0xF) << (4 * s);
@@ -434,7 +459,7 @@ __global__ void q4_untile_mma_kernel(const uint32_t* __restrict__ tiled, uint8_t
     const int kb = k / KB, kl = k % KB, c = kl >> 4, k16 = kl & 15;
     const int hi8 = k16 >> 3, t = (k16 & 7) >> 1, odd = k16 & 1;
     const int rb = o / RB, rl = o % RB, g = rl & 7, r8 = rl >> 3;
-    const int s = (hi8 << 1 | r8) + 4 * odd;
+    const int s = (r8 << 1 | hi8) + 4 * odd;
     const uint32_t w = tiled[(((size_t)rb * n_kb + kb) * 32 + (g * 4 + t)) * 4 + c];
     b |= (uint8_t)(((w >> (4 * s)) & 0xF) << (4 * nr));
   }

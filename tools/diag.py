@@ -662,6 +662,34 @@ def sec_timeline():
                   f"{(int(t[25, 0]) - int(t[20, 0])) / 1e3:.2f} us")
 
 
+def sec_precision():
+    """How far the batch-1 kernel's fp32 accumulation is from exact arithmetic, in bf16 ulps of the result:
+    fraction of outputs that differ from the correctly rounded fp64 result, and the largest distance."""
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    for N, K in [(4096, 4096), (4096, 11008), (2048, 22016)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=3)
+        qm, qt = tile_mma(L, qw, N, K), (tile(L, qw, N, K) if K <= 11008 else None)
+        g = torch.Generator(device="cpu").manual_seed(5)
+        base = torch.randn(1, K, generator=g)
+        spike = base.clone(); spike[0, 16 * 7 + 2] = 60.0; spike[0, 16 * 90 + 11] = -45.0
+        for name, xf in [("randn", base), ("randn+0.5", base + 0.5), ("|randn|", base.abs()), ("spikes", spike)]:
+            x = xf.to(dev).bfloat16()
+            want = ref_linear(x, lv, sc, z)
+            wb = want.float().bfloat16()
+            ulp = torch.maximum(want.abs(), torch.tensor(1e-30, device=dev, dtype=torch.float64)).log2().floor().sub(7).exp2()
+            y, err = gemv_call(L, x, qm, sc, z, N, K)
+            assert err is None, err
+            line = f"N={N} K={K} x={name:10s} gemv: differ {float((y != wb).float().mean()):.4f}  max |y-exact| {float(((y.double() - want).abs() / ulp).max()):.3f} ulp"
+            if qt is not None:
+                y2, err = tc_call(L, torch.cat([x, x]), qt, sc, z, N, K)
+                assert err is None, err
+                line += f" | tcgen05: differ {float((y2[0:1] != wb).float().mean()):.4f}  max {float(((y2[0:1].double() - want).abs() / ulp).max()):.3f} ulp"
+            print(line, flush=True)
+
+
 def main():
     which = sys.argv[1:] or SECTIONS
     if len(which) == 1 and os.environ.get("B2L_DIAG_CHILD") == "1":
