@@ -275,6 +275,15 @@ int b2l_decode_step_launches(const b2l_decode_args* args);
 int b2l_debug_mma_rate(void* out, int n_mma, int n_acc, int a_from_smem, int rounds,
                        b2l_stream_t stream);
 
+/* Debug only (tools/diag.py hmma_rate): issue rate of mma.sync.m16n8k16 (f16, fp32 accumulate) on one SM:
+ * one CTA of `warps` warps, `chains` (1, 2, 4, 8) independent accumulators per warp, iters x 8 MMAs per warp,
+ * optionally preceded by the batch-1 kernel's 5 unpack ALU ops.  out: device uint64[2], out[0] = cycles. */
+int b2l_debug_hmma_rate(void* out, int warps, int chains, int iters, int with_unpack, b2l_stream_t stream);
+
+/* Debug only (tools/diag.py cta_times): per-CTA stamps of the last b2l_q4_gemv launch that had a trace buffer
+ * attached.  out: device uint64[n_cta][4] = {activations ready (ns), main loop done (ns), SM id, stages}. */
+int b2l_debug_gemv_cta_times(void* out, int n_cta, b2l_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

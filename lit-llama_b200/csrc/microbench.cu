@@ -92,6 +92,59 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(unsigned long long* out, 
 }  // namespace b2l
 
 // out: uint64[rounds * 3] = {issue cycles of n_mma MMAs, commit issue cycles, total cycles until the commit arrives}
+// ---- legacy tensor pipe: how often can one SM sub-partition issue mma.sync.m16n8k16 (HMMA.16816.F32)?
+// One CTA, `warps` warps, each with CH independent accumulator chains; optionally the 5 ALU ops per MMA
+// of the int4 unpack (1 shift + 4 LOP3 per word) in front of every MMA.
+template <int CH>
+__global__ void __launch_bounds__(1024) hmma_rate_kernel(unsigned long long* out, int iters, int with_unpack, uint32_t seed) {
+  float acc[CH][4];
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+  uint32_t w = seed + threadIdx.x;
+  uint32_t a0 = 0x3c003c00u, a1 = 0x3c003c00u, a2 = 0x3c003c00u, a3 = 0x3c003c00u;
+  const uint32_t b0 = 0x3c003c00u, b1 = 0x3c003c00u;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (with_unpack) {
+        const uint32_t w8 = w >> 8;
+        asm volatile("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xEA;" : "=r"(a0) : "r"(w));
+        asm volatile("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xEA;" : "=r"(a1) : "r"(w8));
+        asm volatile("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xEA;" : "=r"(a2) : "r"(w));
+        asm volatile("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xEA;" : "=r"(a3) : "r"(w8));
+        w += 0x01010101u;
+      }
+      asm volatile(
+          "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+          : "+f"(acc[j % CH][0]), "+f"(acc[j % CH][1]), "+f"(acc[j % CH][2]), "+f"(acc[j % CH][3])
+          : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  float sink = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) sink += acc[c][0] + acc[c][1] + acc[c][2] + acc[c][3];
+  if (threadIdx.x == 0) { out[0] = (unsigned long long)(t1 - t0); out[1] = (unsigned long long)__float_as_uint(sink); }
+}
+
+extern "C" int b2l_debug_hmma_rate(void* out, int warps, int chains, int iters, int with_unpack, b2l_stream_t stream) {
+  B2L_CHECK_ARG(out && warps > 0 && warps <= 32 && iters > 0 && (chains == 1 || chains == 2 || chains == 4 || chains == 8),
+                "b2l_debug_hmma_rate: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* o = (unsigned long long*)out;
+  if (chains == 1) hmma_rate_kernel<1><<<1, warps * 32, 0, st>>>(o, iters, with_unpack, 0x12345678u);
+  else if (chains == 2) hmma_rate_kernel<2><<<1, warps * 32, 0, st>>>(o, iters, with_unpack, 0x12345678u);
+  else if (chains == 4) hmma_rate_kernel<4><<<1, warps * 32, 0, st>>>(o, iters, with_unpack, 0x12345678u);
+  else hmma_rate_kernel<8><<<1, warps * 32, 0, st>>>(o, iters, with_unpack, 0x12345678u);
+  B2L_LAUNCH_CHECK("hmma_rate_kernel");
+  return 0;
+}
+
 extern "C" int b2l_debug_mma_rate(void* out, int n_mma, int n_acc, int a_from_smem, int rounds, b2l_stream_t stream) {
   B2L_CHECK_ARG(out && n_mma > 0 && n_acc > 0 && n_acc <= 8 && rounds > 0, "b2l_debug_mma_rate: bad argument");
   b2l::mma_rate_kernel<<<1, 128, 0, (cudaStream_t)stream>>>((unsigned long long*)out, n_mma, n_acc, a_from_smem, rounds);

@@ -62,6 +62,10 @@ struct Params {
   int nocompute;           // debug: consumers release every stage untouched (pure TMA streaming rate)
 };
 
+// debug (tools/diag.py cta_times, only written when a trace buffer is attached): per CTA
+// {x_ready ns, loop_done ns, %smid, stages streamed}
+__device__ unsigned long long g_cta_dbg[1024 * 4];
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
@@ -147,6 +151,28 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
+}
+
+// One k-block position (64 k) of NH 16-row halves: LDS.128 per half, 1 shift + 4 LOP3 per word, 4 MMAs per half.
+template <int NH>
+__device__ __forceinline__ void kblock_mma(float (&acc)[MAX_HALVES][2][4], const uint8_t* wbase, const uint4& xa, const uint4& xb,
+                                           uint32_t kmask, uint32_t kmask4, uint32_t kmagic) {
+  const uint32_t bb[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const uint4 wv = *reinterpret_cast<const uint4*>(wbase + h * HALF_STAGE_BYTES);
+    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t a[4];
+      const uint32_t w8 = ww[c] >> 8;
+      a[0] = lop_and_or(ww[c], kmask, kmagic);   // row g,     k 2t..2t+1     : 1024 + q
+      a[1] = lop_and_or(w8, kmask, kmagic);      // row g + 8, k 2t..2t+1     : 1024 + q
+      a[2] = lop_and_or(ww[c], kmask4, kmagic);  // row g,     k 2t+8..2t+9   : 1024 + 16 q  (x / 16 in B)
+      a[3] = lop_and_or(w8, kmask4, kmagic);     // row g + 8, k 2t+8..2t+9   : 1024 + 16 q
+      mma_f16_16816(acc[h][c & 1], a, bb[2 * c], bb[2 * c + 1]);
+    }
+  }
 }
 
 // MAXC = activation chunks (2048 elements each) a thread block caches in registers during the prologue:
@@ -296,7 +322,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
       for (int o = 16; o > 1; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
       if (lane < 2) red[8 + 8 * lane + warp] = sx;   // the epilogue warp adds the 8 partials of each class in a fixed order
       named_bar_sync(3, NT + 32);          // releases the epilogue warp too: xf and the partial sums are ready
-      if (tid == 0) { tl_max(p.tl, 2); if (p.tl != nullptr) atomicMin(p.tl + 60, globaltimer_ns()); }
+      if (tid == 0) {
+        tl_max(p.tl, 2);
+        if (p.tl != nullptr) {
+          atomicMin(p.tl + 60, globaltimer_ns());
+          if (blockIdx.x < 1024) g_cta_dbg[blockIdx.x * 4] = globaltimer_ns();
+        }
+      }
     }
 
     // ---- weights: stage -> registers -> mma.sync.  Warp w takes k-block positions w and w + 8 of a stage
@@ -327,29 +359,31 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
         mbar_wait(bar_full + slot * 8, phase);
         if (p.tl != nullptr && blockIdx.x == 0 && tid == 0 && dbg_it < 12) p.tl[8 + 2 * dbg_it] = globaltimer_ns();
         const uint8_t* st_base = smem + L.ring + slot * STAGE_BYTES + lane * 16;
+        if (nkb == KBP_PER_STAGE && !p.nocompute) {
+          // the common case (full stage), branch-free for two halves and for one
+          if (halves == MAX_HALVES) {
 #pragma unroll
-        for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
-          const int kbl = i * NCW + warp;  // k-block position inside the stage
-          if (kbl < nkb && !p.nocompute) {
-            const uint4* xp = reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * 128);
-            const uint4 xa = xp[0], xb = xp[1];
-            const uint32_t bb[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
+              const int kbl = i * NCW + warp;
+              const uint4* xp = reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * 128);
+              kblock_mma<MAX_HALVES>(acc, st_base + kbl * KB_BYTES, xp[0], xp[1], kmask, kmask4, kmagic);
+            }
+          } else {
 #pragma unroll
-            for (int h = 0; h < MAX_HALVES; ++h) {
-              if (h < halves) {
-                const uint4 wv = *reinterpret_cast<const uint4*>(st_base + h * HALF_STAGE_BYTES + kbl * KB_BYTES);
-                const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+            for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
+              const int kbl = i * NCW + warp;
+              const uint4* xp = reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * 128);
+              kblock_mma<1>(acc, st_base + kbl * KB_BYTES, xp[0], xp[1], kmask, kmask4, kmagic);
+            }
+          }
+        } else if (!p.nocompute) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  uint32_t a[4];
-                  const uint32_t w8 = ww[c] >> 8;
-                  a[0] = lop_and_or(ww[c], kmask, kmagic);   // row g,     k 2t..2t+1     : 1024 + q
-                  a[1] = lop_and_or(w8, kmask, kmagic);      // row g + 8, k 2t..2t+1     : 1024 + q
-                  a[2] = lop_and_or(ww[c], kmask4, kmagic);  // row g,     k 2t+8..2t+9   : 1024 + 16 q  (x / 16 in B)
-                  a[3] = lop_and_or(w8, kmask4, kmagic);     // row g + 8, k 2t+8..2t+9   : 1024 + 16 q
-                  mma_f16_16816(acc[h][c & 1], a, bb[2 * c], bb[2 * c + 1]);
-                }
-              }
+          for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
+            const int kbl = i * NCW + warp;  // k-block position inside the stage
+            if (kbl < nkb) {
+              const uint4* xp = reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * 128);
+              if (halves == MAX_HALVES) kblock_mma<MAX_HALVES>(acc, st_base + kbl * KB_BYTES, xp[0], xp[1], kmask, kmask4, kmagic);
+              else kblock_mma<1>(acc, st_base + kbl * KB_BYTES, xp[0], xp[1], kmask, kmask4, kmagic);
             }
           }
         }
@@ -373,7 +407,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
       __syncwarp();
       named_bar_arrive(6 + buf, NCW * 32 + 32);  // partials of this unit are in the scratch buffer
     }
-    if (tid == 0) { tl_max(p.tl, 3); if (p.tl != nullptr) atomicMin(p.tl + 61, globaltimer_ns()); }
+    if (tid == 0) {
+      tl_max(p.tl, 3);
+      if (p.tl != nullptr) {
+        atomicMin(p.tl + 61, globaltimer_ns());
+        if (blockIdx.x < 1024) {
+          uint32_t smid;
+          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          g_cta_dbg[blockIdx.x * 4 + 1] = globaltimer_ns();
+          g_cta_dbg[blockIdx.x * 4 + 2] = smid;
+          g_cta_dbg[blockIdx.x * 4 + 3] = (unsigned long long)total_stages;
+        }
+      }
+    }
   } else {
     // ===================== epilogue warp: lane = row of the 32-row unit =====================
     pdl_wait();
@@ -492,6 +538,13 @@ extern "C" int b2l_q4_untile_mma(const void* qw_tiled, void* qw, int N, int K, b
   const size_t total = (size_t)(K / 2) * N;
   q4_untile_mma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)qw_tiled, (uint8_t*)qw, N, K);
   B2L_LAUNCH_CHECK("q4_untile_mma_kernel");
+  return 0;
+}
+
+extern "C" int b2l_debug_gemv_cta_times(void* out, int n_cta, b2l_stream_t stream) {
+  B2L_CHECK_ARG(out && n_cta > 0 && n_cta <= 1024, "b2l_debug_gemv_cta_times: bad argument");
+  B2L_CUDA(cudaMemcpyFromSymbolAsync(out, g_cta_dbg, (size_t)n_cta * 4 * sizeof(unsigned long long), 0, cudaMemcpyDeviceToDevice,
+                                     (cudaStream_t)stream));
   return 0;
 }
 

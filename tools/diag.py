@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_step_int8", "timeline"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "hmma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_step_int8", "timeline"]
 
 
 def rand_q4(N, K, dev, seed=0, sz_dtype=None, groups=1, bits=4):
@@ -477,6 +477,68 @@ def sec_mma_rate():
                       f"commit_issue={r[1]:.0f} total_until_arrive={r[2]:.0f} ({r[2] / n_mma:.1f}/mma)")
 
 
+def sec_hmma_rate():
+    """Legacy tensor pipe: cycles per mma.sync.m16n8k16 per SM sub-partition, by warps / chains / unpack."""
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    out = torch.zeros(2, dtype=torch.int64, device=dev)
+    iters = 512
+    for unpack in (0, 1):
+        for warps in (4, 8, 16, 20):
+            for chains in (1, 2, 4, 8):
+                L.check(L.lib().b2l_debug_hmma_rate(out.data_ptr(), warps, chains, iters, unpack, L.stream_ptr()), "hmma_rate")
+                torch.cuda.synchronize()
+                L.check(L.lib().b2l_debug_hmma_rate(out.data_ptr(), warps, chains, iters, unpack, L.stream_ptr()), "hmma_rate")
+                torch.cuda.synchronize()
+                cyc = int(out[0])
+                per_smsp = (warps / 4) * iters * 8
+                print(f"unpack={unpack} warps={warps:2d} chains={chains}: {cyc} cycles, {cyc / (iters * 8):.1f} clk per MMA per warp, "
+                      f"{cyc / per_smsp:.2f} clk per MMA per sub-partition", flush=True)
+
+
+def sec_cta_times():
+    """Per-CTA main-loop times of one batch-1 launch per 7B shape: who are the stragglers?"""
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    lib = L.lib()
+    for (name, N, K) in [("c_attn", 12288, 4096), ("fc12", 22016, 4096), ("mlp_proj", 4096, 11008)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=3)
+        qts = [tile_mma(L, qw, N, K) for _ in range(6)]   # rotate copies: weights come from HBM, not L2
+        x = torch.randn(1, K, device=dev).bfloat16()
+        y = torch.zeros(1, N, device=dev, dtype=torch.bfloat16)
+        tl = torch.zeros(64, dtype=torch.int64, device=dev)
+        out = torch.zeros((296, 4), dtype=torch.int64, device=dev)
+        for rep in range(6):
+            tl.zero_(); tl[0] = 2**62; tl[60] = 2**62; tl[61] = 2**62
+            a = L.Q4LinearArgs(x=x.data_ptr(), ldx=K, qw_tiled=qts[rep].data_ptr(), scales=sc.data_ptr(), zeros=z.data_ptr(), sz_dtype=0,
+                               y=y.data_ptr(), ldy=N, M=1, N=N, K=K, prologue=0, norm_scale=None, eps=1e-5, epilogue=0, res=None,
+                               ldres=N, split_k=0, flags=0, trace=tl.data_ptr())
+            L.check(lib.b2l_q4_gemv(C.byref(a), L.stream_ptr()), "gemv")
+            torch.cuda.synchronize()
+        L.check(lib.b2l_debug_gemv_cta_times(out.data_ptr(), 296, L.stream_ptr()), "cta_times")
+        torch.cuda.synchronize()
+        o = out.cpu()
+        t0 = int(o[:, 0].min())
+        loop = (o[:, 1] - o[:, 0]).double() / 1e3
+        per_stage = loop / o[:, 3].double().clamp_min(1)
+        print(f"--- {name}: loop us min {float(loop.min()):.2f} median {float(loop.median()):.2f} max {float(loop.max()):.2f}; "
+              f"stages per CTA {int(o[:, 3].min())}..{int(o[:, 3].max())}; us/stage min {float(per_stage.min()):.3f} median {float(per_stage.median()):.3f} max {float(per_stage.max()):.3f}")
+        # by SM: the two CTAs of an SM, their stage counts and finish times
+        by_sm = {}
+        for c in range(296):
+            by_sm.setdefault(int(o[c, 2]), []).append((c, int(o[c, 3]), (int(o[c, 1]) - t0) / 1e3))
+        rows = sorted(by_sm.items(), key=lambda kv: -max(v[2] for v in kv[1]))
+        print(f"    SMs used {len(by_sm)}; CTAs per SM histogram {sorted(set(len(v) for v in by_sm.values()))}")
+        for sm, v in rows[:6] + rows[-4:]:
+            print(f"    sm {sm:3d}: " + "  ".join(f"cta {c:3d} stages {st:2d} done@{t:.2f}" for c, st, t in v))
+        hist = torch.histc(loop.float(), bins=8, min=float(loop.min()), max=float(loop.max()))
+        print(f"    loop-time histogram ({float(loop.min()):.2f}..{float(loop.max()):.2f} us, 8 bins): {[int(h) for h in hist]}")
+
+
 def sec_trace():
     """clock64 stamps of CTA 0 of one launch: where does a CTA spend its time?"""
     import torch
@@ -573,6 +635,35 @@ def sec_bench_step():
                 torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / 60 * 1e3
             print(f"decode step 7B pos~16-80 pdl={pdl} graph={graph_after > 0}: {us:.1f} us/token  {1e6 / us:.1f} tok/s")
+
+
+def sec_bench_ctx():
+    """Decode step time against context length (graph + PDL): what single-token attention costs."""
+    import torch
+    from bench import build_synthetic_model
+
+    dev = torch.device("cuda")
+    model = build_synthetic_model("7B", dev)
+    S = 2048
+    model.copy_logits = False
+    tok = torch.randint(0, 32000, (1, 1), device=dev, dtype=torch.int32)
+    with torch.no_grad():
+        model(torch.randint(0, 32000, (1, 16), device=dev, dtype=torch.int32), S, torch.arange(16, device=dev))
+        t16 = None
+        for p0 in (16, 120, 136, 512, 1024, 1536, 1990):
+            pos = [torch.tensor([p0 + i], device=dev) for i in range(48)]
+            for i in range(6):
+                model(tok, S, pos[i])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(6, 46):
+                model(tok, S, pos[i])
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 40 * 1e3
+            t16 = t16 or us
+            print(f"decode step 7B pos~{p0 + 6}-{p0 + 46}: {us:.1f} us/token  (+{(us - t16) / 32:.2f} us per layer over pos 16)")
 
 
 def sec_bench_step_int8():

@@ -1,2 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
-timeout 300 python bench.py 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_gpu_quant.py -m gpu -q -k gemv 2>&1 | tail -2
+timeout 300 python tools/diag.py bench_step 2>&1 | grep "decode step" | head -1
+timeout 300 python tools/diag.py cta_times 2>&1 | grep "^---"
