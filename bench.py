@@ -119,13 +119,13 @@ class ClockSampler:
 
 def sample_next(logits, top_k=TOP_K, temperature=TEMPERATURE):
     """generate.py:68-76 as lit_llama_b200.generate() runs it on the GPU (fused temperature /
-    top-k / softmax kernel + torch.multinomial); the CPU baseline keeps the reference's torch ops."""
+    top-k / softmax / draw kernel on torch's Exp(1) noise = torch.multinomial's sample); the CPU baseline keeps the reference's torch ops."""
     import torch
 
     if logits.is_cuda:
-        from lit_llama_b200 import sample_probs
+        from lit_llama_b200 import sample_token
 
-        return torch.multinomial(sample_probs(logits[0, -1], temperature, top_k), num_samples=1)
+        return sample_token(logits[0, -1], temperature, top_k)
     logits = logits[0, -1] / temperature
     v, _ = torch.topk(logits, min(top_k, logits.size(-1)))
     logits = torch.where(logits < v[[-1]], -float("Inf"), logits)

@@ -176,6 +176,14 @@ int b2l_q8_outlier_mask(const void* x, int ldx, int M, int K, float threshold, v
 int b2l_topk_softmax(const void* logits, float temperature, int top_k, void* probs, int V,
                      b2l_stream_t stream);
 
+/* generate.py:68-76 in one launch: the probabilities above AND the draw of generate.py:76
+ * (torch.multinomial(probs, num_samples=1)).  For one draw ATen computes argmax(probs / q), q ~ Exp(1)
+ * (ATen/native/Distributions.cpp, ties to the lower index); `noise` is that q, bf16 [V], drawn by the caller with
+ * torch (`torch.empty_like(probs).exponential_(1)`: the RNG consumption of multinomial), so `*token` (device
+ * int64) equals the reference's sample for the same generator state.  probs may be NULL. */
+int b2l_topk_softmax_sample(const void* logits, float temperature, int top_k, const void* noise, void* probs,
+                            int64_t* token, int V, b2l_stream_t stream);
+
 /* ------------------------------------------------------------------------------
  * CausalSelfAttention.forward without the two linears, model.py:197-232:
  * split qkv, apply_rope(q), apply_rope(k) (model.py:306-323), append k,v to the

@@ -16,16 +16,40 @@ from .model import LLaMA
 from .utils import llama_model_lookup, quantization
 
 
+_TORCH_MULTINOMIAL = torch.multinomial
+
+
 def sample_probs(logits_row: torch.Tensor, temperature: float = 1.0, top_k: Optional[int] = None) -> torch.Tensor:
     """generate.py:68-75: probabilities of the next token from the last position's logits
     (V,) bf16: temperature, top-k filter and softmax fused in one kernel (b2l_topk_softmax)."""
     L.require_cuda_bf16(logits_row, "sample_probs")
     x = logits_row.contiguous()
+    if x.data_ptr() % 16:
+        x = x.clone()  # the kernel reads 16-byte vectors
     V = x.numel()
     probs = torch.empty_like(x)
     k = 0 if top_k is None else min(int(top_k), V)
     L.check(L.lib().b2l_topk_softmax(x.data_ptr(), float(temperature), k, probs.data_ptr(), V, L.stream_ptr()), "b2l_topk_softmax")
     return probs
+
+
+def sample_token(logits_row: torch.Tensor, temperature: float = 1.0, top_k: Optional[int] = None) -> torch.Tensor:
+    """generate.py:68-76: the next token (shape (1,), int64) drawn from the last position's logits.
+    `torch.multinomial(probs, num_samples=1)` is `argmax(probs / q)` with `q = empty_like(probs).exponential_(1)`
+    (ATen/native/Distributions.cpp); q is drawn here with torch -- the RNG consumption of multinomial, so for the same
+    generator state the token equals `torch.multinomial(sample_probs(...), 1)` -- and everything else is one
+    launch (b2l_topk_softmax_sample) instead of multinomial's dozen."""
+    L.require_cuda_bf16(logits_row, "sample_token")
+    x = logits_row.contiguous()
+    if x.data_ptr() % 16:
+        x = x.clone()  # the kernel reads 16-byte vectors
+    V = x.numel()
+    q = torch.empty_like(x).exponential_(1)
+    token = torch.empty(1, dtype=torch.int64, device=x.device)
+    k = 0 if top_k is None else min(int(top_k), V)
+    L.check(L.lib().b2l_topk_softmax_sample(x.data_ptr(), float(temperature), k, q.data_ptr(), None, token.data_ptr(), V, L.stream_ptr()),
+            "b2l_topk_softmax_sample")
+    return token
 
 
 @torch.no_grad()
@@ -54,8 +78,12 @@ def generate(
     for _ in range(max_new_tokens):
         x = idx.index_select(0, input_pos).view(1, -1)
         logits = model(x, max_seq_length, input_pos)
-        probs = sample_probs(logits[0, -1], temperature, top_k)  # generate.py:68-75 in one launch
-        idx_next = torch.multinomial(probs, num_samples=1).to(dtype=dtype)
+        if torch.multinomial is _TORCH_MULTINOMIAL:
+            idx_next = sample_token(logits[0, -1], temperature, top_k).to(dtype=dtype)  # generate.py:68-76: RNG draw + one launch
+        else:
+            # torch.multinomial has been replaced (the reference's tests/test_generate.py:26-54 patches it to record
+            # the draws): keep calling it, on the fused probabilities
+            idx_next = torch.multinomial(sample_probs(logits[0, -1], temperature, top_k), num_samples=1).to(dtype=dtype)
         input_pos = input_pos[-1:] + 1
         idx = idx.index_copy(0, input_pos, idx_next)
         if eos_id is not None and idx_next == eos_id:

@@ -22,3 +22,15 @@ def load_golden(name):
     import torch
 
     return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+@pytest.fixture(autouse=True)
+def _seed_per_test(request):
+    """Every test draws from its own fixed random stream: rounding-boundary statistics (fractions of bit-equal
+    outputs) are then the same on every run."""
+    import zlib
+
+    import torch
+
+    torch.manual_seed(zlib.crc32(request.node.nodeid.encode()) & 0x7FFFFFFF)
+    yield

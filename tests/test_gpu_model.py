@@ -238,6 +238,27 @@ def test_fused_sampling_head_matches_torch_ops(dev):
         assert abs(float(got.float().sum()) - 1.0) < 2e-2
 
 
+def test_fused_draw_equals_torch_multinomial(dev):
+    """b2l_topk_softmax_sample: for the same generator state the token is the one `torch.multinomial(probs, 1)`
+    draws from the kernel's own probabilities (generate.py:76) -- multinomial is argmax(probs / Exp(1) noise)."""
+    import lit_llama_b200 as P
+
+    for V, k, temp in [(32000, 200, 0.8), (32000, None, 1.0), (32003, 50, 0.7), (130, 4, 2.0), (1000, 1000, 1.3)]:
+        for trial in range(12):
+            logits = (torch.randn(V, device=dev) * (1 + trial % 4)).bfloat16()
+            torch.manual_seed(1000 + trial)
+            want = torch.multinomial(P.sample_probs(logits, temp, k), num_samples=1)
+            torch.manual_seed(1000 + trial)
+            got = P.sample_token(logits, temp, k)
+            assert got.shape == (1,) and got.dtype == torch.int64
+            assert int(got) == int(want), (V, k, trial)
+    # the same RNG consumption as multinomial: the generator is in the same state afterwards
+    logits = torch.randn(32000, device=dev).bfloat16()
+    torch.manual_seed(5); torch.multinomial(P.sample_probs(logits, 0.8, 200), 1); a = torch.rand(4, device=dev)
+    torch.manual_seed(5); P.sample_token(logits, 0.8, 200); b = torch.rand(4, device=dev)
+    assert torch.equal(a, b)
+
+
 def test_llm_int8_model_vs_oracle(dev):
     """--quantize llm.int8: tiny model, prefill + decode, against the oracle restatement."""
     from gpu_util import build_tiny
