@@ -392,7 +392,7 @@ def main():
                        "l2": "weights 3.31 GB per token >> 126 MB L2 (inputs larger than L2)"},
             "clocks": clk,
             "e2e": {"value": aggregate_throughput(world, Ke, t_e2e), "unit": "tokens/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 8, "steps": Ke},
-            "gpu_launches": launches * K,
+            "gpu_launches": (launches + 1) * K,  # b2l_decode_step's kernels + the fused sampling kernel, per token
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "kernel": q4_name, "launches_per_token": n_q4, "bytes_per_token_launches": W,
                          "peak_source": which,
