@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "hmma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_step_int8", "timeline"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "hmma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "bench_step_int8", "timeline"]
 
 
 def rand_q4(N, K, dev, seed=0, sz_dtype=None, groups=1, bits=4):
@@ -664,6 +664,70 @@ def sec_bench_ctx():
             us = e0.elapsed_time(e1) / 40 * 1e3
             t16 = t16 or us
             print(f"decode step 7B pos~{p0 + 6}-{p0 + 46}: {us:.1f} us/token  (+{(us - t16) / 32:.2f} us per layer over pos 16)")
+
+
+def _decode_us(model, B, S, dev, p0=512, n=24):
+    import torch
+
+    tok = torch.randint(0, 32000, (B, 1), device=dev, dtype=torch.int32)
+    pos = [torch.tensor([p0 + i], device=dev) for i in range(n + 6)]
+    with torch.no_grad():
+        for i in range(6):
+            model(tok, S, pos[i])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(6, 6 + n):
+            model(tok, S, pos[i])
+        e1.record()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+def sec_bench_13b_b8():
+    """BASELINE.json configs[3]: LLaMA-13B gptq.int4, batch 8, prefill 512 then decode (ctx 2048)."""
+    import torch
+    from bench import build_synthetic_model
+
+    dev = torch.device("cuda")
+    model = build_synthetic_model("13B", dev)
+    model.copy_logits = False
+    B, T, S = 8, 512, 2048
+    idx = torch.randint(0, 32000, (B, T), device=dev, dtype=torch.int32)
+    with torch.no_grad():
+        for rep in range(2):
+            model.reset_cache()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model(idx, S, torch.arange(T, device=dev))
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+        print(f"13B gptq.int4 prefill B={B} T={T}: {ms:.1f} ms  ({B * T / ms * 1e3:.0f} tokens/s; dequant + library GEMM branch)")
+    us = _decode_us(model, B, S, dev, p0=T)
+    print(f"13B gptq.int4 decode B={B} pos~{T}: {us:.0f} us/step  {B * 1e6 / us:.0f} tokens/s  (tcgen05 kernel, M={B})")
+
+
+def sec_bench_sizes():
+    """Batch-1 decode of every LLaMA size the reference names (lit_llama/model.py llama_configs)."""
+    import torch
+    from bench import build_synthetic_model
+
+    dev = torch.device("cuda")
+    for name in ("13B", "30B", "65B"):
+        model = build_synthetic_model(name, dev)
+        model.copy_logits = False
+        with torch.no_grad():
+            model(torch.randint(0, 32000, (1, 16), device=dev, dtype=torch.int32), 2048, torch.arange(16, device=dev))
+        us = _decode_us(model, 1, 2048, dev, p0=16, n=32)
+        cfg = model.config
+        nh = [m for m in model.transformer.h[0].mlp.modules() if hasattr(m, "quant_weight")][0].quant_weight.shape[0]
+        w_bytes = cfg.n_layer * (4 * cfg.n_embd * cfg.n_embd + 3 * cfg.n_embd * nh) // 2 + cfg.padded_vocab_size * cfg.n_embd // 2
+        print(f"{name} gptq.int4 decode B=1 pos~16-50: {us:.0f} us/token  {1e6 / us:.1f} tok/s  "
+              f"({w_bytes / us / 1e3:.0f} GB/s of packed weights = {w_bytes / us / 1e3 / 6573.2:.3f} of measured HBM peak)")
+        del model
+        torch.cuda.empty_cache()
 
 
 def sec_bench_step_int8():
