@@ -169,20 +169,26 @@ def test_7b_shaped_block_vs_oracle(dev):
     torch.testing.assert_close(v[:, :, :8].float().cpu(), exact.kv[0][1].float(), rtol=2 ** -6, atol=2e-2)
 
 
-def test_fused_attention_equals_unfused(dev):
-    """head_size 128 single-token attention: the fused kernel (rope + append + split-S +
-    ticketed merge) against the three-kernel path on identical inputs, at several positions
-    including a full cache and the roll branch."""
+@pytest.mark.parametrize("S,cases", [
+    (300, [(0, 0), (5, 0), (127, 0), (128, 0), (299, 0), (300, 0), (333, 7)]),          # 3 splits
+    (128, [(0, 0), (127, 0), (130, 3)]),                                                 # single split
+    (256, [(100, 0), (128, 0), (255, 0), (256, 5)]),                                     # 2 splits
+    (2048, [(3, 0), (129, 0), (1023, 0), (1024, 0), (1500, 0), (2047, 0), (2050, 11)]),  # 16 splits
+])
+def test_fused_attention_equals_unfused(dev, S, cases):
+    """head_size 128 single-token attention: the fused kernel (rope + append + split-S + ticketed
+    merge) against the three-kernel path on identical inputs, at several positions including a full
+    cache and the roll branch."""
     from lit_llama_b200 import _lib as L
 
-    B, nh, hs, S, blk = 2, 8, 128, 300, 512
+    B, nh, hs, blk = 2, 8, 128, max(512, S)
     C = nh * hs
     lib = L.lib()
     g = torch.Generator(device=dev).manual_seed(3)
     rope = O.rope_table(blk, hs).to(dev)
     kc = (torch.randn(B, nh, S, hs, device=dev, generator=g) * 0.5).bfloat16()
     vc = (torch.randn(B, nh, S, hs, device=dev, generator=g) * 0.5).bfloat16()
-    for pos, ring0 in [(0, 0), (5, 0), (127, 0), (128, 0), (299, 0), (300, 0), (333, 7)]:
+    for pos, ring0 in cases:
         qkv = torch.randn(B, 1, 3 * C, device=dev, generator=g).bfloat16()
         outs = []
         for flags in (0, 8):
