@@ -209,7 +209,7 @@ def run_reference(args, rank, world):
 
 
 def time_q4_launches(model, dev):
-    """Every launch of the tcgen05 int4 linear kernel of one token, back to back (all
+    """Every launch of the batch-1 int4 linear kernel (q4_gemv_kernel) of one token, back to back (all
     layers' distinct weights: 3.3 GB, far beyond L2), timed with CUDA events."""
     import ctypes as C
 

@@ -90,6 +90,9 @@ def test_no_cpu_fallback_anywhere():
             mod(x)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         P.apply_rope(torch.zeros(1, 3, 2, 32, dtype=torch.bfloat16), torch.zeros(3, 16, 2))
+    for fn in (P.sample_probs, P.sample_token):   # the sampling tail of generate() has no CPU path either
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fn(torch.zeros(64, dtype=torch.bfloat16), 0.8, 4)
 
 
 def test_product_does_not_import_the_oracle():

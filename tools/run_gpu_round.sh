@@ -1,4 +1,3 @@
-timeout 120 python -m pytest tests/test_gpu_model.py -m gpu -q -x -k "fused_attention" 2>&1 | tail -3
-timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -3
-timeout 200 python tools/diag.py bench_ctx 2>&1 | grep "decode step"
-B2L_ATTN_CLUSTER=1 timeout 200 python tools/diag.py bench_ctx 2>&1 | grep "decode step" | sed -n '2p;4p;5p'
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1
