@@ -104,6 +104,9 @@ typedef struct b2l_q4_linear_args {
   int flags;            /* B2L_F_*                                                    */
   void* trace;          /* debug: device uint64[256] receiving clock64() stamps of CTA 0
                            (NULL = off); see tools/diag.py `trace`                     */
+  void* workspace;      /* b2l_q4_gemv_batch only: b2l_q4_gemv_batch_workspace_bytes(K) bytes of device
+                           scratch, 16-byte aligned (activation fragments; may be shared by all
+                           launches of one stream)                                       */
 } b2l_q4_linear_args;
 
 enum {
@@ -131,6 +134,15 @@ size_t b2l_q4_tiled_mma_bytes(int N, int K);
 int b2l_q4_tile_mma(const void* qw, void* qw_tiled, int N, int K, b2l_stream_t stream);
 int b2l_q4_untile_mma(const void* qw_tiled, void* qw, int N, int K, b2l_stream_t stream);
 int b2l_q4_gemv(const b2l_q4_linear_args* args, b2l_stream_t stream);
+
+/* The same fused linear for 1..8 activation rows (batched decode), same weight tiling (b2l_q4_tile_mma) and
+ * argument block as b2l_q4_gemv plus `workspace`; x [M, K] with leading dimension ldx (ldx % 8 == 0), y / res
+ * with ldy / ldres.  An mma.m16n8k16 tile has 8 columns: activation row n is column n, so 8 rows cost the MMAs
+ * of one.  Two launches: the rows are normalised and converted to MMA fragment order once
+ * (q4_batch_prep_kernel), then streamed stage by stage next to the weights (q4_gemv_batch_kernel).
+ * Replaces the same reference code as b2l_q4_gemv for B > 1 (model.py:76-122 accepts any batch). */
+size_t b2l_q4_gemv_batch_workspace_bytes(int K);
+int b2l_q4_gemv_batch(const b2l_q4_linear_args* args, b2l_stream_t stream);
 
 /* ------------------------------------------------------------------------------
  * model.py element-wise pieces (used by the module-level drop-ins and by prefill)
@@ -271,6 +283,9 @@ typedef struct b2l_decode_args {
   int flags;                 /* B2L_F_*                                               */
   void* timeline;            /* debug: device uint64[(5*n_layer+1)*64] of %globaltimer stamps per
                                 launch (NULL = off); tools/diag.py `timeline`           */
+  void* batch_work;          /* B in 2..8: scratch of b2l_q4_gemv_batch_workspace_bytes(max K) bytes; the
+                                linears then run on the mma.sync batch kernel (weights need qw_mma).
+                                NULL: tcgen05 kernel (weights need qw_tiled)              */
 } b2l_decode_args;
 
 int b2l_decode_step(const b2l_decode_args* args, b2l_stream_t stream);

@@ -25,7 +25,7 @@ class Q4LinearArgs(C.Structure):
         ("M", c_int), ("N", c_int), ("K", c_int),
         ("prologue", c_int), ("norm_scale", c_void_p), ("eps", c_float),
         ("epilogue", c_int), ("res", c_void_p), ("ldres", c_int),
-        ("split_k", c_int), ("flags", c_int), ("trace", c_void_p),
+        ("split_k", c_int), ("flags", c_int), ("trace", c_void_p), ("workspace", c_void_p),
     ]
 
 
@@ -50,7 +50,7 @@ class DecodeArgs(C.Structure):
         ("idx", c_void_p), ("idx_is_i64", c_int),
         ("input_pos", c_void_p), ("ring_start", c_void_p), ("block_size", c_int),
         ("x", c_void_p), ("qkv", c_void_p), ("att", c_void_p), ("hid", c_void_p), ("attn_work", c_void_p),
-        ("logits", c_void_p), ("flags", c_int), ("timeline", c_void_p),
+        ("logits", c_void_p), ("flags", c_int), ("timeline", c_void_p), ("batch_work", c_void_p),
     ]
 
 
@@ -69,6 +69,8 @@ _SIGS = {
     "b2l_q4_tile_mma": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b2l_q4_untile_mma": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b2l_q4_gemv": (c_int, [C.POINTER(Q4LinearArgs), c_void_p]),
+    "b2l_q4_gemv_batch": (c_int, [C.POINTER(Q4LinearArgs), c_void_p]),
+    "b2l_q4_gemv_batch_workspace_bytes": (c_size_t, [c_int]),
     "b2l_rmsnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "b2l_embedding": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2l_silu_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

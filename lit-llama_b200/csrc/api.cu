@@ -62,11 +62,12 @@ extern "C" int b2l_device_info(int* sm, int* cc_major, int* cc_minor) {
 // ---------------------------------------------------------------------------------
 static int q4_call(const b2l_q4_weight& w, const void* x, int ldx, void* y, int ldy, int M, int sz_dtype, int prologue,
                    const void* norm_scale, float eps, int epilogue, const void* res, int ldres, int flags,
-                   b2l_stream_t stream, void* trace = nullptr) {
+                   b2l_stream_t stream, void* trace = nullptr, void* batch_work = nullptr) {
   b2l_q4_linear_args a{};
   a.x = x; a.ldx = ldx;
   const bool gemv = (M == 1 && w.qw_mma != nullptr);
-  a.qw_tiled = gemv ? w.qw_mma : w.qw_tiled; a.scales = w.scales; a.zeros = w.zeros; a.sz_dtype = sz_dtype;
+  const bool batch = (!gemv && M <= 8 && w.qw_mma != nullptr && batch_work != nullptr);
+  a.qw_tiled = (gemv || batch) ? w.qw_mma : w.qw_tiled; a.scales = w.scales; a.zeros = w.zeros; a.sz_dtype = sz_dtype;
   a.y = y; a.ldy = ldy;
   a.M = M; a.N = w.N; a.K = w.K;
   a.prologue = prologue; a.norm_scale = norm_scale; a.eps = eps;
@@ -75,6 +76,10 @@ static int q4_call(const b2l_q4_weight& w, const void* x, int ldx, void* y, int 
   a.flags = flags;
   a.trace = gemv ? trace : nullptr;
   if (gemv) return b2l_q4_gemv(&a, stream);
+  if (batch) {
+    a.workspace = batch_work;
+    return b2l_q4_gemv_batch(&a, stream);
+  }
   if (a.qw_tiled == nullptr) {
     set_error("b2l_decode_step: weight has no tiling for batch %d", M);
     return B2L_E_STATE;
@@ -85,7 +90,8 @@ static int q4_call(const b2l_q4_weight& w, const void* x, int ldx, void* y, int 
 extern "C" int b2l_decode_step_launches(const b2l_decode_args* d) {
   if (!d) return 0;
   const int attn = (d->n_embd / d->n_head == 128) ? 1 : 3;  // fused single-token attention for head_size 128
-  return 2 + d->n_layer * (4 + attn) + 1;  // ring advance + embedding, per Block 4 linears + attention, ln_f+lm_head
+  const int lin = (d->B > 1 && d->B <= 8 && d->batch_work) ? 2 : 1;  // the batch kernel is two launches per linear
+  return 2 + d->n_layer * (4 * lin + attn) + lin;  // ring advance + embedding, per Block 4 linears + attention, ln_f+lm_head
 }
 
 extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {
@@ -109,7 +115,7 @@ extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {
   for (int l = 0; l < d->n_layer; ++l) {
     const b2l_layer& L = d->layers[l];
     if ((rc = q4_call(L.c_attn, d->x, C, d->qkv, 3 * C, B, d->sz_dtype, B2L_PRO_RMSNORM, L.rms_1, d->eps, B2L_EPI_STORE,
-                      nullptr, 0, fl, stream, tl())))
+                      nullptr, 0, fl, stream, tl(), d->batch_work)))
       return rc;
     g_attn_timeline = tl();
     if ((rc = b2l_attention(d->qkv, L.k_cache, L.v_cache, d->rope, d->input_pos, d->ring_start, d->att, d->attn_work, B,
@@ -119,15 +125,15 @@ extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {
     }
     g_attn_timeline = nullptr;
     if ((rc = q4_call(L.c_proj, d->att, C, d->x, C, B, d->sz_dtype, B2L_PRO_NONE, nullptr, 0.f, B2L_EPI_RESIDUAL, d->x, C,
-                      fl, stream, tl())))
+                      fl, stream, tl(), d->batch_work)))
       return rc;
     if ((rc = q4_call(L.c_fc12, d->x, C, d->hid, d->n_hidden, B, d->sz_dtype, B2L_PRO_RMSNORM, L.rms_2, d->eps,
-                      B2L_EPI_SWIGLU, nullptr, 0, fl, stream, tl())))
+                      B2L_EPI_SWIGLU, nullptr, 0, fl, stream, tl(), d->batch_work)))
       return rc;
     if ((rc = q4_call(L.mlp_proj, d->hid, d->n_hidden, d->x, C, B, d->sz_dtype, B2L_PRO_NONE, nullptr, 0.f,
-                      B2L_EPI_RESIDUAL, d->x, C, fl, stream, tl())))
+                      B2L_EPI_RESIDUAL, d->x, C, fl, stream, tl(), d->batch_work)))
       return rc;
   }
   return q4_call(d->lm_head, d->x, C, d->logits, d->vocab, B, d->sz_dtype, B2L_PRO_RMSNORM, d->ln_f, d->eps,
-                 B2L_EPI_STORE, nullptr, 0, fl, stream, tl());
+                 B2L_EPI_STORE, nullptr, 0, fl, stream, tl(), d->batch_work);
 }

@@ -246,7 +246,13 @@ class _DecodeState:
         self.work = torch.zeros(lib.b2l_attn_workspace_bytes(B, nh, hs, 1, S) // 4 + 1, device=device, dtype=torch.float32)
         self.keep = []  # tensors the argument block points into
 
-        gemv = (B == 1)  # batch 1: mma.sync kernel and its tiling; batch 2..16: tcgen05 kernel and its tiling
+        from .quantization import BATCH_GEMV, batch_workspace
+
+        # batch 1..8: mma.sync kernels (q4_gemv / q4_gemv_batch) and their tiling; 9..16: tcgen05 kernel and its tiling
+        gemv = (B == 1) or (B <= 8 and BATCH_GEMV)
+        self.batch_ws = None
+        if gemv and B > 1:
+            self.batch_ws = batch_workspace(device, max(C_, n_hidden))
 
         def q4(lin: ColBlockQuantizedLinear) -> L.Q4Weight:
             t = lin.tiled_mma() if gemv else lin.tiled()
@@ -280,7 +286,8 @@ class _DecodeState:
             idx_is_i64=1 if idx_dtype == torch.int64 else 0, input_pos=self.pos.data_ptr(),
             ring_start=model._ring.data_ptr(), block_size=cfg.block_size, x=self.x.data_ptr(), qkv=self.qkv.data_ptr(),
             att=self.att.data_ptr(), hid=self.hid.data_ptr(), attn_work=self.work.data_ptr(),
-            logits=self.logits.data_ptr(), flags=model.decode_flags)
+            logits=self.logits.data_ptr(), flags=model.decode_flags,
+            batch_work=None if self.batch_ws is None else self.batch_ws.data_ptr())
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.calls = 0
 

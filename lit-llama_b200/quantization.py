@@ -7,11 +7,30 @@
 is no Triton, no dense fallback and no CPU path.
 """
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
 
 from . import _lib as L
+
+
+# 2..8 activation rows go through the mma.sync batch kernel (B2L_BATCH_GEMV=0: tcgen05 kernel instead)
+BATCH_GEMV = os.environ.get("B2L_BATCH_GEMV", "1") != "0"
+_BATCH_WS = {}
+_BATCH_WS_OLD = []
+
+
+def batch_workspace(device, K: int) -> torch.Tensor:
+    """Scratch of b2l_q4_gemv_batch (activation fragments), one per device, grown to the largest K seen.
+    Launches of one stream are serialised, so every layer can share it."""
+    need = L.lib().b2l_q4_gemv_batch_workspace_bytes(int(K))
+    ws = _BATCH_WS.get(device)
+    if ws is None or ws.numel() < need:
+        if ws is not None:
+            _BATCH_WS_OLD.append(ws)  # captured CUDA graphs may still point at it: never freed
+        ws = _BATCH_WS[device] = torch.zeros(need, dtype=torch.uint8, device=device)
+    return ws
 
 
 class ColBlockQuantizedLinear(torch.nn.Module):
@@ -142,6 +161,14 @@ class ColBlockQuantizedLinear(torch.nn.Module):
                 zeros=self.zeros.data_ptr(), sz_dtype=L.sz_dtype_of(self.scales), y=y.data_ptr(), ldy=N, M=1, N=N, K=K,
                 prologue=L.PRO_NONE, norm_scale=None, eps=0.0, epilogue=L.EPI_STORE, res=None, ldres=0, split_k=0, flags=0)
             L.check(L.lib().b2l_q4_gemv(C.byref(a), L.stream_ptr()), "b2l_q4_gemv")
+        elif self.gemv_capable and aligned and M <= 8 and BATCH_GEMV:
+            # 2..8 rows: the mma.sync tile has 8 columns, one per row (csrc/q4_gemv_batch.cu)
+            a = L.Q4LinearArgs(
+                x=x.data_ptr(), ldx=x.stride(0), qw_tiled=self.tiled_mma().data_ptr(), scales=self.scales.data_ptr(),
+                zeros=self.zeros.data_ptr(), sz_dtype=L.sz_dtype_of(self.scales), y=y.data_ptr(), ldy=N, M=M, N=N, K=K,
+                prologue=L.PRO_NONE, norm_scale=None, eps=0.0, epilogue=L.EPI_STORE, res=None, ldres=0, split_k=0, flags=0,
+                workspace=batch_workspace(inp.device, K).data_ptr())
+            L.check(L.lib().b2l_q4_gemv_batch(C.byref(a), L.stream_ptr()), "b2l_q4_gemv_batch")
         elif self.tc_capable and aligned and M <= 64:
             qt = self.tiled()
             for m0 in range(0, M, 16):

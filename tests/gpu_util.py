@@ -7,7 +7,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-from diag import gemv_call, rand_q4, ref_linear, relerr, tc_call, tile, tile_mma  # noqa: E402,F401
+from diag import gemv_batch_call, gemv_call, rand_q4, ref_linear, relerr, tc_call, tile, tile_mma  # noqa: E402,F401
 
 
 def build_tiny(dev, cfg, mode="gptq.int4", seed=1234, tile_cols=-1, exact_linears=False):

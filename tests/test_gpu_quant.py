@@ -145,6 +145,56 @@ def test_gemv_prologue_epilogue_and_determinism(dev):
         assert torch.equal(y0, y1)
 
 
+@pytest.mark.parametrize("N,K,M,grid", [(4096, 4096, 8, 0), (4096, 11008, 5, 0), (22016, 4096, 2, 0), (130, 256, 3, 0), (48, 4096, 8, 2),
+                                         (16, 64, 1, 0), (5120, 13824, 8, 0), (4096, 4096, 7, 100)])
+def test_gemv_batch_vs_exact_and_vs_batch1(dev, N, K, M, grid):
+    """The 2..8-row kernel: every row against exact arithmetic, and BIT-identical to the batch-1 kernel on
+    that row (same MMAs, same fixed reduction order; only the activations travel differently)."""
+    from gpu_util import assert_q4_linear_close, gemv_batch_call, gemv_call, rand_q4, tile_mma
+    from lit_llama_b200 import _lib as L
+
+    lv, qw, sc, z = rand_q4(N, K, dev, seed=N + K + M)
+    qt = tile_mma(L, qw, N, K)
+    x = torch.randn(M, K, device=dev).bfloat16()
+    y, err = gemv_batch_call(L, x, qt, sc, z, N, K, grid=grid)
+    assert err is None, err
+    assert_q4_linear_close(y, x, lv, sc, z)
+    for m in range(M):
+        y1, err = gemv_call(L, x[m : m + 1].contiguous(), qt, sc, z, N, K, grid=grid)
+        assert err is None, err
+        assert torch.equal(y[m : m + 1], y1), m
+
+
+def test_gemv_batch_prologue_epilogue(dev):
+    from gpu_util import gemv_batch_call, gemv_call, rand_q4, tile_mma
+    from lit_llama_b200 import _lib as L
+
+    N, K, M = 512, 1024, 6
+    lv, qw, sc, z = rand_q4(N, K, dev, seed=5)
+    qt = tile_mma(L, qw, N, K)
+    x = (torch.randn(M, K, device=dev) * 0.7).bfloat16()
+    g = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
+    res = torch.randn(M, N, device=dev).bfloat16()
+    for kw in (dict(prologue=1, norm_scale=g), dict(epilogue=1, res=res), dict(prologue=1, norm_scale=g, epilogue=2, n_out=N // 2)):
+        y, err = gemv_batch_call(L, x, qt, sc, z, N, K, **kw)
+        assert err is None, err
+        for m in range(M):   # the batch-1 kernel (itself checked against the reference formulas) row by row
+            kw1 = dict(kw)
+            if "res" in kw1:
+                kw1["res"] = res[m : m + 1].contiguous()
+            y1, err = gemv_call(L, x[m : m + 1].contiguous(), qt, sc, z, N, K, **kw1)
+            assert err is None, err
+            assert torch.equal(y[m : m + 1], y1), (kw.keys(), m)
+    # in place on the residual stream (x + h with y aliasing res), twice the same result
+    buf = res.clone()
+    y, _ = gemv_batch_call(L, x, qt, sc, z, N, K, epilogue=1, res=res)
+    _, err = gemv_batch_call(L, x, qt, sc, z, N, K, epilogue=1, res=buf, y=buf)
+    assert err is None and torch.equal(buf, y)
+    # argument checks
+    _, err = gemv_batch_call(L, torch.zeros(9, K, device=dev, dtype=torch.bfloat16), qt, sc, z, N, K)
+    assert err is not None and "M=9" in err
+
+
 @pytest.mark.parametrize("name,N,K", [("13B c_attn", 15360, 5120), ("13B mlp_proj", 5120, 13824), ("65B c_proj", 8192, 8192),
                                       ("65B mlp_proj", 8192, 22016)])
 def test_gemv_13b_65b_shapes(dev, name, N, K):

@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "hmma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "bench_step_int8", "timeline"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "hmma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline"]
 
 
 def rand_q4(N, K, dev, seed=0, sz_dtype=None, groups=1, bits=4):
@@ -100,6 +100,27 @@ def gemv_call(L, x, qt, scales, zeros, N, K, *, y=None, prologue=0, norm_scale=N
     rc = L.lib().b2l_q4_gemv(C.byref(a), L.stream_ptr())
     if rc != 0:
         return None, f"rc={rc}: {L.lib().b2l_last_error().decode()}"
+    return y, None
+
+
+def gemv_batch_call(L, x, qt, scales, zeros, N, K, *, y=None, prologue=0, norm_scale=None, eps=1e-5, epilogue=0, res=None, grid=0,
+                    flags=0, n_out=None):
+    """b2l_q4_gemv_batch on x (M, K), M <= 8."""
+    import torch
+
+    M = x.shape[0]
+    n_out = n_out or N
+    if y is None:
+        y = torch.zeros((M, n_out), device=x.device, dtype=torch.bfloat16)
+    ws = torch.zeros(L.lib().b2l_q4_gemv_batch_workspace_bytes(K), dtype=torch.uint8, device=x.device)
+    a = L.Q4LinearArgs(x=x.data_ptr(), ldx=x.stride(0), qw_tiled=qt.data_ptr(), scales=scales.data_ptr(), zeros=zeros.data_ptr(),
+                       sz_dtype=L.sz_dtype_of(scales), y=y.data_ptr(), ldy=n_out, M=M, N=N, K=K, prologue=prologue,
+                       norm_scale=None if norm_scale is None else norm_scale.data_ptr(), eps=eps, epilogue=epilogue,
+                       res=None if res is None else res.data_ptr(), ldres=N, split_k=grid, flags=flags, workspace=ws.data_ptr())
+    rc = L.lib().b2l_q4_gemv_batch(C.byref(a), L.stream_ptr())
+    if rc != 0:
+        return None, f"rc={rc}: {L.lib().b2l_last_error().decode()}"
+    torch.cuda.synchronize()
     return y, None
 
 
@@ -706,7 +727,9 @@ def sec_bench_13b_b8():
             ms = e0.elapsed_time(e1)
         print(f"13B gptq.int4 prefill B={B} T={T}: {ms:.1f} ms  ({B * T / ms * 1e3:.0f} tokens/s; dequant + library GEMM branch)")
     us = _decode_us(model, B, S, dev, p0=T)
-    print(f"13B gptq.int4 decode B={B} pos~{T}: {us:.0f} us/step  {B * 1e6 / us:.0f} tokens/s  (tcgen05 kernel, M={B})")
+    from lit_llama_b200.quantization import BATCH_GEMV
+    print(f"13B gptq.int4 decode B={B} pos~{T}: {us:.0f} us/step  {B * 1e6 / us:.0f} tokens/s  "
+          f"({'mma.sync batch kernel' if BATCH_GEMV else 'tcgen05 kernel'}, M={B})")
 
 
 def sec_bench_sizes():
@@ -728,6 +751,34 @@ def sec_bench_sizes():
               f"({w_bytes / us / 1e3:.0f} GB/s of packed weights = {w_bytes / us / 1e3 / 6573.2:.3f} of measured HBM peak)")
         del model
         torch.cuda.empty_cache()
+
+
+def sec_batch_debug():
+    """B = 2 decode on the tiny model: batch kernel vs batch-1 kernel, with and without PDL / fast path."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gpu_util import build_tiny
+
+    dev = torch.device("cuda")
+    cfg = dict(block_size=32, vocab_size=96, n_layer=2, n_head=4, n_embd=128)
+    idx = torch.tensor([[3, 17, 40], [9, 9, 1]], device=dev)
+    for flags in (1, 0):
+        for fast in (True, False):
+            model, _, _ = build_tiny(dev, cfg)
+            model.decode_flags = flags
+            model.graph_after = 0
+            if not fast:
+                model._fast_ok = False
+            with torch.no_grad():
+                pre2 = model(idx, 16, torch.arange(3, device=dev)).clone()
+                both = model(torch.tensor([[5], [60]], device=dev), 16, torch.tensor([3], device=dev)).clone()
+                model.reset_cache()
+                if not fast:
+                    model._fast_ok = False
+                pre1 = model(idx[1:], 16, torch.arange(3, device=dev)).clone()
+                one = model(torch.tensor([[60]], device=dev), 16, torch.tensor([3], device=dev)).clone()
+            print(f"pdl={flags} fast={fast}: prefill row diff {float((pre2[1:].float() - pre1.float()).abs().max()):.4g}  "
+                  f"decode row diff {float((both[1:].float() - one.float()).abs().max()):.4g}  (|logits| max {float(one.float().abs().max()):.3g})", flush=True)
 
 
 def sec_bench_step_int8():
