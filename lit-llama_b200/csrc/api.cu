@@ -23,14 +23,15 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int sm_count() {
-  static int n = 0;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  });
-  return n;
+  static int n[B2L_MAX_DEVICES] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= B2L_MAX_DEVICES) return 148;
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
+  }
+  return n[dev];
 }
 
 }  // namespace b2l

@@ -525,11 +525,8 @@ extern "C" int b2l_attention(void* qkv, void* k_cache, void* v_cache, const void
   if (T == 1 && head_size == 128 && !(flags & B2L_F_ROPE_ROWS) && !(flags & B2L_F_ATTN_UNFUSED)) {
     const int n_split = (S + FD_CHUNK - 1) / FD_CHUNK;
     int* tickets = reinterpret_cast<int*>(reinterpret_cast<char*>(work) + ws_partials_bytes(B, n_head, head_size, T, S));
-    static bool smem_set = false;
-    if (!smem_set) {
-      B2L_CUDA(cudaFuncSetAttribute(attn_decode_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FD_SMEM_BYTES));
-      smem_set = true;
-    }
+    static DynSmemCache smem_cache;
+    if (int rc = ensure_dyn_smem(attn_decode_fused_kernel, FD_SMEM_BYTES, smem_cache)) return rc;
     LaunchCfg lc(dim3(B * n_head, n_split), dim3(FD_WARPS * 32), FD_SMEM_BYTES, st, (flags & B2L_F_PDL) != 0);
     B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, attn_decode_fused_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_cache,
                                 (__nv_bfloat16*)v_cache, (const float*)rope, input_pos, ring_start, (__nv_bfloat16*)y,

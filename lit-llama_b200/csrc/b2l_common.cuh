@@ -44,7 +44,27 @@ int cuda_fail(cudaError_t e, const char* what);  // records + returns (int)e
     if (e_ != cudaSuccess) return b2l::cuda_fail(e_, "launch " name); \
   } while (0)
 
-int sm_count();  // cached
+int sm_count();  // of the current device, cached per device
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember per device what a kernel was given.
+constexpr int B2L_MAX_DEVICES = 64;
+struct DynSmemCache {
+  size_t bytes[B2L_MAX_DEVICES] = {};
+};
+template <typename Kernel>
+inline int ensure_dyn_smem(Kernel kernel, size_t bytes, DynSmemCache& cache) {
+  int dev = 0;
+  B2L_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= B2L_MAX_DEVICES) {
+    B2L_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+  }
+  if (bytes > cache.bytes[dev]) {
+    B2L_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cache.bytes[dev] = bytes;
+  }
+  return 0;
+}
 
 // ---- small device helpers ----
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }

@@ -483,12 +483,9 @@ extern "C" int b2l_q4_gemv(const b2l_q4_linear_args* a, b2l_stream_t stream) {
   p.nst = nst;
   const SmemLayout L = smem_layout(nst, a->K);
   const bool wide = a->K > 6 * NCW * 32 * 8;
-  static size_t configured_smem[2] = {0, 0};
-  if (L.total > configured_smem[wide]) {
-    if (wide) B2L_CUDA(cudaFuncSetAttribute(q4_gemv_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    else B2L_CUDA(cudaFuncSetAttribute(q4_gemv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    configured_smem[wide] = L.total;
-  }
+  static DynSmemCache smem_cache[2];
+  if (int rc = wide ? ensure_dyn_smem(q4_gemv_kernel<12>, L.total, smem_cache[1]) : ensure_dyn_smem(q4_gemv_kernel<6>, L.total, smem_cache[0]))
+    return rc;
   int grid = a->split_k > 0 ? a->split_k : (env_cps > 0 ? env_cps : 2) * sm_count();  // split_k doubles as a grid override
   if (grid > p.n_rb) grid = p.n_rb;
   LaunchCfg lc(dim3(grid), dim3(NTHREADS), L.total, (cudaStream_t)stream, (a->flags & B2L_F_PDL) != 0, 1);

@@ -372,11 +372,8 @@ extern "C" int b2l_q4_gemv_batch(const b2l_q4_linear_args* a, b2l_stream_t strea
   p.epilogue = a->epilogue; p.res = (const __nv_bfloat16*)a->res; p.ldres = a->ldres;
   p.nst = BMAX_STAGES;
   const BSmem L = bsmem_layout(p.nst);
-  static size_t configured_smem = 0;
-  if (L.total > configured_smem) {
-    B2L_CUDA(cudaFuncSetAttribute(q4_gemv_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    configured_smem = L.total;
-  }
+  static DynSmemCache smem_cache;
+  if (int rc = ensure_dyn_smem(q4_gemv_batch_kernel, L.total, smem_cache)) return rc;
   int grid = a->split_k > 0 ? a->split_k : 2 * sm_count();   // split_k doubles as a grid override
   if (grid > p.n_rb) grid = p.n_rb;
   LaunchCfg lc(dim3(grid), dim3(NTHREADS), L.total, st, pdl, 1);

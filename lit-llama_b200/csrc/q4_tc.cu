@@ -691,11 +691,8 @@ extern "C" int b2l_q4_linear_tc(const b2l_q4_linear_args* a, b2l_stream_t stream
   const SmemLayout L = smem_layout(p.nst_ring, p.kseg_max, p.kcb, p.M);
   B2L_CHECK_SUPPORTED(L.total <= 200 * 1024, "b2l_q4_linear_tc: shared memory %u B too large (K=%d, split_k=%d)", L.total, a->K, S);
 
-  static size_t configured_smem = 0;
-  if (L.total > configured_smem) {
-    B2L_CUDA(cudaFuncSetAttribute(q4_linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    configured_smem = L.total;
-  }
+  static DynSmemCache smem_cache;
+  if (int rc = ensure_dyn_smem(q4_linear_tc_kernel, L.total, smem_cache)) return rc;
   LaunchCfg lc(dim3(n_tiles * S), dim3(NTHREADS), L.total, (cudaStream_t)stream, (a->flags & B2L_F_PDL) != 0, S);
   B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, q4_linear_tc_kernel, p));
   return 0;

@@ -337,11 +337,8 @@ extern "C" int b2l_q8_gemv(const void* x, const void* w_tiled, const void* cb, c
   if (nst < 2) nst = 2;
   p.nst = nst;
   const SmemLayout L = smem_layout(nst, K);
-  static size_t configured = 0;
-  if (L.total > configured) {
-    B2L_CUDA(cudaFuncSetAttribute(q8_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    configured = L.total;
-  }
+  static DynSmemCache smem_cache;
+  if (int rc = ensure_dyn_smem(q8_gemv_kernel, L.total, smem_cache)) return rc;
   int grid = 2 * sm_count();
   if (grid > p.n_rb) grid = p.n_rb;
   LaunchCfg lc(dim3(grid), dim3(NTHREADS), L.total, (cudaStream_t)stream, (flags & B2L_F_PDL) != 0, 1);

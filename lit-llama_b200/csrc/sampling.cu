@@ -287,11 +287,9 @@ static int launch_topk(const void* logits, float temperature, int top_k, void* p
   const size_t Vp = ((size_t)V + 7) & ~(size_t)7;
   const size_t smem = Vp * 2 * (noise != nullptr ? 2 : 1);
   B2L_CHECK_SUPPORTED(smem <= 200 * 1024, "%s: vocabulary %d too large for one CTA", who, V);
-  static size_t configured = 0;
-  if (smem > configured && smem > 48 * 1024) {
-    B2L_CUDA(cudaFuncSetAttribute(topk_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static DynSmemCache smem_cache;
+  if (smem > 48 * 1024)
+    if (int rc = ensure_dyn_smem(topk_softmax_kernel, smem, smem_cache)) return rc;
   topk_softmax_kernel<<<1, SAMP_THREADS, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, 1.0f / temperature, top_k,
                                                                       (__nv_bfloat16*)probs, (const __nv_bfloat16*)noise,
                                                                       (long long*)token, V);
