@@ -148,3 +148,35 @@ def test_linear8bitlt_contract_on_cpu():
     assert torch.equal(lin.weight.data, cb) and torch.equal(lin.weight.SCB, scb)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         lin(torch.zeros(1, 256, dtype=torch.bfloat16))
+
+
+def test_empty_init_on_device_and_lazy_load(tmp_path):
+    """utils.py:73-138 and :332-344: construction context and lazy checkpoint loading (host-side, CPU)."""
+    from lit_llama_b200.utils import EmptyInitOnDevice, lazy_load
+
+    before = (torch.nn.Linear, torch.get_default_dtype(), torch.nn.init.normal_)
+    with EmptyInitOnDevice(device=torch.device("cpu"), dtype=torch.bfloat16, quantization_mode="gptq.int4"):
+        m = P.LLaMA(P.LLaMAConfig(block_size=16, vocab_size=64, n_layer=1, n_head=2, n_embd=64))
+        lin = torch.nn.Linear(8, 4, bias=False)
+    assert (torch.nn.Linear, torch.get_default_dtype(), torch.nn.init.normal_) == before   # everything restored
+    assert isinstance(m.lm_head, P.ColBlockQuantizedLinear) and isinstance(lin, P.ColBlockQuantizedLinear)
+    assert m.transformer.wte.weight.dtype == torch.bfloat16
+    with pytest.raises(ValueError, match="only supported on the GPU"):
+        EmptyInitOnDevice(device=torch.device("cpu"), quantization_mode="llm.int8")
+    with pytest.raises(RuntimeError, match="unknown quantization mode"):
+        EmptyInitOnDevice(quantization_mode="int3")
+
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    for v in sd.values():
+        if v.dtype == torch.uint8:
+            v.random_(0, 256)
+        else:
+            v.copy_(torch.randn(v.shape))
+    path = tmp_path / "ckpt.pth"
+    torch.save(sd, path)
+    with lazy_load(path) as ck:
+        assert set(ck) == set(sd)
+        assert P.llama_model_lookup({"transformer.wte.weight": torch.empty(1, 4096)}) == "7B"
+        m.load_state_dict(ck)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]) and v.stride() == sd[k].stride(), k
