@@ -298,6 +298,11 @@ int b2l_decode_step_launches(const b2l_decode_args* args);
 int b2l_debug_mma_rate(void* out, int n_mma, int n_acc, int a_from_smem, int rounds,
                        b2l_stream_t stream);
 
+/* Debug only (tools/diag.py mma_issuers): 1..4 warps of one CTA each issue 16 tcgen05.mma (own accumulator) and a
+ * commit.  out: device uint64[rounds][8] = {cycles until warp w's commit arrived (w = 0..3), cycles warp w spent
+ * issuing (w = 0..3)}: does MMA issue scale with the number of issuing threads? */
+int b2l_debug_mma_issuers(void* out, int n_issuers, int rounds, b2l_stream_t stream);
+
 /* Debug only (tools/diag.py hmma_rate): issue rate of mma.sync.m16n8k16 (f16, fp32 accumulate) on one SM:
  * one CTA of `warps` warps, `chains` (1, 2, 4, 8) independent accumulators per warp, iters x 8 MMAs per warp,
  * optionally preceded by the batch-1 kernel's 5 unpack ALU ops.  out: device uint64[2], out[0] = cycles. */

@@ -89,6 +89,72 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(unsigned long long* out, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
+
+// ---- can several threads of one CTA keep the tensor pipe fed better than one?  `n_issuers` warps (1..4) each
+// elect lane 0 to issue 16 back-to-back 128x16x16 tcgen05.mma (A in TMEM, shared; own 16-column accumulator) and
+// one commit on their own mbarrier.  out[r * 8 + w] = cycles from the common start until warp w's commit arrived,
+// out[r * 8 + 4 + w] = cycles warp w spent issuing.  If the per-warp time does not grow with n_issuers, MMA issue
+// is a per-thread limit and a multi-issuer kernel scales; if it grows linearly it is a per-SM limit.
+__global__ void __launch_bounds__(128) mma_multi_issuer_kernel(unsigned long long* out, int n_issuers, int rounds) {
+  __shared__ __align__(128) uint8_t bsm[16 * 1024];
+  __shared__ __align__(8) unsigned long long bars[4];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 16 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(bsm)[i] = 0x3f803f80u;  // bf16 1.0
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(q4tc::mb_smem_u32(&bars[i])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(q4tc::mb_smem_u32(&tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+  {
+    uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t v = 0x3f803f80u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(v) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t sb = q4tc::mb_smem_u32(bsm);
+  const uint64_t bdesc = (uint64_t)((sb & 0x3FFFFu) >> 4) | ((uint64_t)(256 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+  const uint32_t bar_a = q4tc::mb_smem_u32(&bars[warp]);
+  const uint32_t d = tmem + 64 + (uint32_t)(warp * 16);
+  uint32_t parity = 0;
+  for (int r = 0; r < rounds; ++r) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp < n_issuers && lane == 0) {
+      const long long t0 = clock64();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+                     "r"(tmem), "l"(bdesc), "r"(idesc), "r"(i > 0 ? 1u : 0u) : "memory");
+      const long long t1 = clock64();
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_a) : "memory");
+      uint32_t ok;
+      do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar_a), "r"(parity) : "memory");
+      } while (!ok);
+      const long long t2 = clock64();
+      out[r * 8 + warp] = (unsigned long long)(t2 - t0);
+      out[r * 8 + 4 + warp] = (unsigned long long)(t1 - t0);
+    }
+    parity ^= 1;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
 }  // namespace b2l
 
 // out: uint64[rounds * 3] = {issue cycles of n_mma MMAs, commit issue cycles, total cycles until the commit arrives}
@@ -142,6 +208,13 @@ extern "C" int b2l_debug_hmma_rate(void* out, int warps, int chains, int iters, 
   else if (chains == 4) hmma_rate_kernel<4><<<1, warps * 32, 0, st>>>(o, iters, with_unpack, 0x12345678u);
   else hmma_rate_kernel<8><<<1, warps * 32, 0, st>>>(o, iters, with_unpack, 0x12345678u);
   B2L_LAUNCH_CHECK("hmma_rate_kernel");
+  return 0;
+}
+
+extern "C" int b2l_debug_mma_issuers(void* out, int n_issuers, int rounds, b2l_stream_t stream) {
+  B2L_CHECK_ARG(out && n_issuers >= 1 && n_issuers <= 4 && rounds > 0, "b2l_debug_mma_issuers: bad argument");
+  b2l::mma_multi_issuer_kernel<<<1, 128, 0, (cudaStream_t)stream>>>((unsigned long long*)out, n_issuers, rounds);
+  B2L_LAUNCH_CHECK("mma_multi_issuer_kernel");
   return 0;
 }
 

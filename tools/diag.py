@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "hmma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "hmma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline"]
 
 
 def rand_q4(N, K, dev, seed=0, sz_dtype=None, groups=1, bits=4):
@@ -496,6 +496,23 @@ def sec_mma_rate():
                 r = o[3:].float().mean(0)  # skip cold rounds
                 print(f"A_from_{'smem' if a_smem else 'tmem'} n_acc={n_acc} n_mma={n_mma:3d}: issue={r[0]:.0f} cyc ({r[0] / n_mma:.1f}/mma) "
                       f"commit_issue={r[1]:.0f} total_until_arrive={r[2]:.0f} ({r[2] / n_mma:.1f}/mma)")
+
+
+def sec_mma_issuers():
+    """tcgen05.mma issue from 1..4 threads of one CTA at once (round-2 question: does a multi-issuer kernel scale?)."""
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    rounds = 6
+    out = torch.zeros(rounds * 8, dtype=torch.int64, device=dev)
+    for n in (1, 2, 3, 4):
+        out.zero_()
+        L.check(L.lib().b2l_debug_mma_issuers(out.data_ptr(), n, rounds, L.stream_ptr()), "mma_issuers")
+        torch.cuda.synchronize()
+        o = out.view(rounds, 8).cpu()
+        print(f"issuers={n}: last round, cycles until commit per warp {o[-1, :n].tolist()}  issue cycles {o[-1, 4:4 + n].tolist()}  "
+              f"-> {float(o[-1, :n].max()) / (16 * n):.1f} cycles per MMA overall", flush=True)
 
 
 def sec_hmma_rate():
