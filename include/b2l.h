@@ -303,6 +303,11 @@ int b2l_debug_mma_rate(void* out, int n_mma, int n_acc, int a_from_smem, int rou
  * issuing (w = 0..3)}: does MMA issue scale with the number of issuing threads? */
 int b2l_debug_mma_issuers(void* out, int n_issuers, int rounds, b2l_stream_t stream);
 
+/* Debug only (tools/diag.py grid_flag): latency of a grid-wide arrive-and-wait on a global counter (red.release +
+ * ld.acquire polling) with ctas_per_sm * SMs co-resident CTAs.  counter: zeroed device uint32; out: device
+ * uint64[2 * rounds], first half zeroed (max ns per round), second half set to ~0 (min ns per round). */
+int b2l_debug_grid_flag(void* out, void* counter, int ctas_per_sm, int rounds, b2l_stream_t stream);
+
 /* Debug only (tools/diag.py hmma_rate): issue rate of mma.sync.m16n8k16 (f16, fp32 accumulate) on one SM:
  * one CTA of `warps` warps, `chains` (1, 2, 4, 8) independent accumulators per warp, iters x 8 MMAs per warp,
  * optionally preceded by the batch-1 kernel's 5 unpack ALU ops.  out: device uint64[2], out[0] = cycles. */

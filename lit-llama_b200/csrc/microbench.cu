@@ -211,6 +211,34 @@ extern "C" int b2l_debug_hmma_rate(void* out, int warps, int chains, int iters, 
   return 0;
 }
 
+// ---- what does a grid-wide dependency cost without a kernel boundary?  Every CTA (all co-resident) arrives on a
+// global counter with red.release and polls it with ld.acquire until all have arrived; out[r] = max over CTAs of
+// the nanoseconds between its arrival and its release, out[rounds + r] = min.  The persistent-kernel plan of
+// DESIGN.md section 7 replaces five kernel boundaries per Block with five of these.
+__global__ void __launch_bounds__(128) grid_flag_kernel(unsigned long long* out, unsigned int* counter, int rounds) {
+  if (threadIdx.x != 0) return;
+  for (int r = 0; r < rounds; ++r) {
+    const unsigned int target = (unsigned int)(r + 1) * gridDim.x;
+    const unsigned long long t0 = b2l::globaltimer_ns();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    const unsigned long long dt = b2l::globaltimer_ns() - t0;
+    atomicMax(out + r, dt);
+    atomicMin(out + rounds + r, dt);
+  }
+}
+
+extern "C" int b2l_debug_grid_flag(void* out, void* counter, int ctas_per_sm, int rounds, b2l_stream_t stream) {
+  B2L_CHECK_ARG(out && counter && ctas_per_sm >= 1 && ctas_per_sm <= 4 && rounds > 0 && rounds <= 64, "b2l_debug_grid_flag: bad argument");
+  // the caller zero-fills `counter` (uint32) and out[0 .. rounds) and fills out[rounds .. 2 rounds) with ~0
+  grid_flag_kernel<<<ctas_per_sm * b2l::sm_count(), 128, 0, (cudaStream_t)stream>>>((unsigned long long*)out, (unsigned int*)counter, rounds);
+  B2L_LAUNCH_CHECK("grid_flag_kernel");
+  return 0;
+}
+
 extern "C" int b2l_debug_mma_issuers(void* out, int n_issuers, int rounds, b2l_stream_t stream) {
   B2L_CHECK_ARG(out && n_issuers >= 1 && n_issuers <= 4 && rounds > 0, "b2l_debug_mma_issuers: bad argument");
   b2l::mma_multi_issuer_kernel<<<1, 128, 0, (cudaStream_t)stream>>>((unsigned long long*)out, n_issuers, rounds);

@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "hmma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "grid_flag", "hmma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline"]
 
 
 def rand_q4(N, K, dev, seed=0, sz_dtype=None, groups=1, bits=4):
@@ -513,6 +513,23 @@ def sec_mma_issuers():
         o = out.view(rounds, 8).cpu()
         print(f"issuers={n}: last round, cycles until commit per warp {o[-1, :n].tolist()}  issue cycles {o[-1, 4:4 + n].tolist()}  "
               f"-> {float(o[-1, :n].max()) / (16 * n):.1f} cycles per MMA overall", flush=True)
+
+
+def sec_grid_flag():
+    """Grid-wide arrive-and-wait through a global counter: the cost of a dependency without a kernel boundary."""
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    rounds = 16
+    for cps in (1, 2):
+        out = torch.zeros(2 * rounds, dtype=torch.int64, device=dev)
+        out[rounds:] = 2**62
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.check(L.lib().b2l_debug_grid_flag(out.data_ptr(), counter.data_ptr(), cps, rounds, L.stream_ptr()), "grid_flag")
+        torch.cuda.synchronize()
+        o = out.cpu()
+        print(f"ctas_per_sm={cps}: arrive-and-wait ns per round, max over CTAs {o[:rounds].tolist()}  min {o[rounds:].tolist()}", flush=True)
 
 
 def sec_hmma_rate():
