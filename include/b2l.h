@@ -292,27 +292,6 @@ int b2l_decode_step(const b2l_decode_args* args, b2l_stream_t stream);
 /* Number of kernels one b2l_decode_step enqueues (for bench.py's gpu_launches). */
 int b2l_decode_step_launches(const b2l_decode_args* args);
 
-/* Debug only (tools/diag.py): tcgen05.mma issue / completion cycle counts of one CTA.
- * out: device uint64[rounds*3] = {cycles to issue n_mma MMAs, cycles to issue the commit,
- * cycles until the commit's mbarrier arrives}. */
-int b2l_debug_mma_rate(void* out, int n_mma, int n_acc, int a_from_smem, int rounds,
-                       b2l_stream_t stream);
-
-/* Debug only (tools/diag.py mma_issuers): 1..4 warps of one CTA each issue 16 tcgen05.mma (own accumulator) and a
- * commit.  out: device uint64[rounds][8] = {cycles until warp w's commit arrived (w = 0..3), cycles warp w spent
- * issuing (w = 0..3)}: does MMA issue scale with the number of issuing threads? */
-int b2l_debug_mma_issuers(void* out, int n_issuers, int rounds, b2l_stream_t stream);
-
-/* Debug only (tools/diag.py grid_flag): latency of a grid-wide arrive-and-wait on a global counter (red.release +
- * ld.acquire polling) with ctas_per_sm * SMs co-resident CTAs.  counter: zeroed device uint32; out: device
- * uint64[2 * rounds], first half zeroed (max ns per round), second half set to ~0 (min ns per round). */
-int b2l_debug_grid_flag(void* out, void* counter, int ctas_per_sm, int rounds, b2l_stream_t stream);
-
-/* Debug only (tools/diag.py hmma_rate): issue rate of mma.sync.m16n8k16 (f16, fp32 accumulate) on one SM:
- * one CTA of `warps` warps, `chains` (1, 2, 4, 8) independent accumulators per warp, iters x 8 MMAs per warp,
- * optionally preceded by the batch-1 kernel's 5 unpack ALU ops.  out: device uint64[2], out[0] = cycles. */
-int b2l_debug_hmma_rate(void* out, int warps, int chains, int iters, int with_unpack, b2l_stream_t stream);
-
 /* Debug only (tools/diag.py cta_times): per-CTA stamps of the last b2l_q4_gemv launch that had a trace buffer
  * attached.  out: device uint64[n_cta][4] = {activations ready (ns), main loop done (ns), SM id, stages}. */
 int b2l_debug_gemv_cta_times(void* out, int n_cta, b2l_stream_t stream);

@@ -89,10 +89,6 @@ _SIGS = {
     "b2l_kv_unroll": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2l_decode_step": (c_int, [C.POINTER(DecodeArgs), c_void_p]),
     "b2l_decode_step_launches": (c_int, [C.POINTER(DecodeArgs)]),
-    "b2l_debug_mma_rate": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "b2l_debug_mma_issuers": (c_int, [c_void_p, c_int, c_int, c_void_p]),
-    "b2l_debug_grid_flag": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "b2l_debug_hmma_rate": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2l_debug_gemv_cta_times": (c_int, [c_void_p, c_int, c_void_p]),
 }
 

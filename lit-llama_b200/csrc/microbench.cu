@@ -1,6 +1,30 @@
-// Debug-only microbenchmarks of the tcgen05 issue/completion costs that size the int4
-// linear's pipeline (tools/diag.py `mma_rate`).  Not on any product path.
+// Debug-only microbenchmarks (tools/diag.py): tcgen05 issue/completion costs, legacy tensor-pipe issue rates,
+// grid-wide flag latency.  Built into libb200diag.so (include/b2l_diag.h), NOT into the product library.
 #include "b2l_common.cuh"
+#include "../../include/b2l_diag.h"
+
+namespace b2l {
+// the diagnostic library carries its own copy of the error state (the product's lives in api.cu)
+static thread_local char g_diag_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_diag_err, sizeof(g_diag_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  (void)cudaGetLastError();
+  return (int)e;
+}
+int sm_count() {
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+  return v;
+}
+}  // namespace b2l
+
+extern "C" const char* b2l_diag_last_error(void) { return b2l::g_diag_err; }
 
 namespace b2l {
 namespace q4tc {
@@ -208,6 +232,59 @@ extern "C" int b2l_debug_hmma_rate(void* out, int warps, int chains, int iters, 
   else if (chains == 4) hmma_rate_kernel<4><<<1, warps * 32, 0, st>>>(o, iters, with_unpack, 0x12345678u);
   else hmma_rate_kernel<8><<<1, warps * 32, 0, st>>>(o, iters, with_unpack, 0x12345678u);
   B2L_LAUNCH_CHECK("hmma_rate_kernel");
+  return 0;
+}
+
+// ---- legacy integer tensor pipe: how often can one SM sub-partition issue mma.sync.m16n8k32 u8 x s8 (IMMA.16832.U8.S8)?
+// Round-2 question: an int8 contraction consumes 512 weight nibbles per MMA (two packed words per lane) with at most
+// two LOP3 in front of it, against 256 nibbles and five ALU ops for the fp16 form.  n_alu = ALU ops issued per MMA.
+template <int CH>
+__global__ void __launch_bounds__(1024) imma_rate_kernel(unsigned long long* out, int iters, int n_alu, uint32_t seed) {
+  int acc[CH][4];
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[c][i] = 0;
+  uint32_t w0 = seed + threadIdx.x, w1 = seed * 3 + threadIdx.x;
+  uint32_t a1 = w0 & 0xf0f0f0f0u, a3 = w1 & 0xf0f0f0f0u;
+  const uint32_t b0 = 0x01020304u, b1 = 0x7f80fe02u;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (n_alu >= 2) {
+        asm volatile("lop3.b32 %0, %1, 0xf0f0f0f0, 0, 0xC0;" : "=r"(a1) : "r"(w0));
+        asm volatile("lop3.b32 %0, %1, 0xf0f0f0f0, 0, 0xC0;" : "=r"(a3) : "r"(w1));
+      }
+      if (n_alu >= 4) {
+        asm volatile("add.u32 %0, %0, 0x01010101;" : "+r"(w0));
+        asm volatile("add.u32 %0, %0, 0x03010101;" : "+r"(w1));
+      }
+      asm volatile(
+          "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+          : "+r"(acc[j % CH][0]), "+r"(acc[j % CH][1]), "+r"(acc[j % CH][2]), "+r"(acc[j % CH][3])
+          : "r"(w0), "r"(a1), "r"(w1), "r"(a3), "r"(b0), "r"(b1));
+    }
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  int sink = 0;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) sink += acc[c][0] + acc[c][1] + acc[c][2] + acc[c][3];
+  if (threadIdx.x == 0) { out[0] = (unsigned long long)(t1 - t0); out[1] = (unsigned long long)(uint32_t)sink; }
+}
+
+extern "C" int b2l_debug_imma_rate(void* out, int warps, int chains, int iters, int n_alu, b2l_stream_t stream) {
+  B2L_CHECK_ARG(out && warps > 0 && warps <= 32 && iters > 0 && (chains == 1 || chains == 2 || chains == 4 || chains == 8),
+                "b2l_debug_imma_rate: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* o = (unsigned long long*)out;
+  if (chains == 1) imma_rate_kernel<1><<<1, warps * 32, 0, st>>>(o, iters, n_alu, 0x12345678u);
+  else if (chains == 2) imma_rate_kernel<2><<<1, warps * 32, 0, st>>>(o, iters, n_alu, 0x12345678u);
+  else if (chains == 4) imma_rate_kernel<4><<<1, warps * 32, 0, st>>>(o, iters, n_alu, 0x12345678u);
+  else imma_rate_kernel<8><<<1, warps * 32, 0, st>>>(o, iters, n_alu, 0x12345678u);
+  B2L_LAUNCH_CHECK("imma_rate_kernel");
   return 0;
 }
 

@@ -14,7 +14,31 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "grid_flag", "hmma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "grid_flag", "hmma_rate", "imma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline"]
+
+
+_DLIB = None
+
+
+def dlib():
+    """tools/libb200diag.so (include/b2l_diag.h): the micro-benchmarks live outside the product library."""
+    global _DLIB
+    if _DLIB is None:
+        h = C.CDLL(os.path.join(ROOT, "tools", "libb200diag.so"))
+        vp, ci = C.c_void_p, C.c_int
+        for name, args in {"b2l_debug_mma_rate": [vp, ci, ci, ci, ci, vp], "b2l_debug_mma_issuers": [vp, ci, ci, vp],
+                           "b2l_debug_grid_flag": [vp, vp, ci, ci, vp], "b2l_debug_hmma_rate": [vp, ci, ci, ci, ci, vp],
+                           "b2l_debug_imma_rate": [vp, ci, ci, ci, ci, vp]}.items():
+            getattr(h, name).restype = ci
+            getattr(h, name).argtypes = args
+        h.b2l_diag_last_error.restype = C.c_char_p
+        _DLIB = h
+    return _DLIB
+
+
+def dcheck(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {dlib().b2l_diag_last_error().decode()}")
 
 
 def rand_q4(N, K, dev, seed=0, sz_dtype=None, groups=1, bits=4):
@@ -490,7 +514,7 @@ def sec_mma_rate():
         for n_acc in (1, 4):
             for n_mma in (1, 4, 16):
                 out.zero_()
-                L.check(L.lib().b2l_debug_mma_rate(out.data_ptr(), n_mma, n_acc, a_smem, 8, L.stream_ptr()), "mma_rate")
+                dcheck(dlib().b2l_debug_mma_rate(out.data_ptr(), n_mma, n_acc, a_smem, 8, L.stream_ptr()), "mma_rate")
                 torch.cuda.synchronize()
                 o = out.cpu().reshape(-1, 3)[:8]
                 r = o[3:].float().mean(0)  # skip cold rounds
@@ -508,7 +532,7 @@ def sec_mma_issuers():
     out = torch.zeros(rounds * 8, dtype=torch.int64, device=dev)
     for n in (1, 2, 3, 4):
         out.zero_()
-        L.check(L.lib().b2l_debug_mma_issuers(out.data_ptr(), n, rounds, L.stream_ptr()), "mma_issuers")
+        dcheck(dlib().b2l_debug_mma_issuers(out.data_ptr(), n, rounds, L.stream_ptr()), "mma_issuers")
         torch.cuda.synchronize()
         o = out.view(rounds, 8).cpu()
         print(f"issuers={n}: last round, cycles until commit per warp {o[-1, :n].tolist()}  issue cycles {o[-1, 4:4 + n].tolist()}  "
@@ -526,7 +550,7 @@ def sec_grid_flag():
         out = torch.zeros(2 * rounds, dtype=torch.int64, device=dev)
         out[rounds:] = 2**62
         counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        L.check(L.lib().b2l_debug_grid_flag(out.data_ptr(), counter.data_ptr(), cps, rounds, L.stream_ptr()), "grid_flag")
+        dcheck(dlib().b2l_debug_grid_flag(out.data_ptr(), counter.data_ptr(), cps, rounds, L.stream_ptr()), "grid_flag")
         torch.cuda.synchronize()
         o = out.cpu()
         print(f"ctas_per_sm={cps}: arrive-and-wait ns per round, max over CTAs {o[:rounds].tolist()}  min {o[rounds:].tolist()}", flush=True)
@@ -543,13 +567,33 @@ def sec_hmma_rate():
     for unpack in (0, 1):
         for warps in (4, 8, 16, 20):
             for chains in (1, 2, 4, 8):
-                L.check(L.lib().b2l_debug_hmma_rate(out.data_ptr(), warps, chains, iters, unpack, L.stream_ptr()), "hmma_rate")
+                dcheck(dlib().b2l_debug_hmma_rate(out.data_ptr(), warps, chains, iters, unpack, L.stream_ptr()), "hmma_rate")
                 torch.cuda.synchronize()
-                L.check(L.lib().b2l_debug_hmma_rate(out.data_ptr(), warps, chains, iters, unpack, L.stream_ptr()), "hmma_rate")
+                dcheck(dlib().b2l_debug_hmma_rate(out.data_ptr(), warps, chains, iters, unpack, L.stream_ptr()), "hmma_rate")
                 torch.cuda.synchronize()
                 cyc = int(out[0])
                 per_smsp = (warps / 4) * iters * 8
                 print(f"unpack={unpack} warps={warps:2d} chains={chains}: {cyc} cycles, {cyc / (iters * 8):.1f} clk per MMA per warp, "
+                      f"{cyc / per_smsp:.2f} clk per MMA per sub-partition", flush=True)
+
+
+def sec_imma_rate():
+    """Legacy integer tensor pipe: cycles per mma.sync.m16n8k32 (u8 x s8) per SM sub-partition, by warps / chains / ALU ops."""
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    out = torch.zeros(2, dtype=torch.int64, device=dev)
+    iters = 512
+    for n_alu in (0, 2, 4):
+        for warps in (4, 8, 16, 20):
+            for chains in (1, 2, 4, 8):
+                for _ in range(2):
+                    dcheck(dlib().b2l_debug_imma_rate(out.data_ptr(), warps, chains, iters, n_alu, L.stream_ptr()), "imma_rate")
+                    torch.cuda.synchronize()
+                cyc = int(out[0])
+                per_smsp = (warps / 4) * iters * 8
+                print(f"n_alu={n_alu} warps={warps:2d} chains={chains}: {cyc} cycles, {cyc / (iters * 8):.1f} clk per MMA per warp, "
                       f"{cyc / per_smsp:.2f} clk per MMA per sub-partition", flush=True)
 
 
