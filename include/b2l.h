@@ -124,24 +124,30 @@ enum {
  * (model.py:166-167, 252). */
 int b2l_q4_linear_tc(const b2l_q4_linear_args* args, b2l_stream_t stream);
 
-/* Batch-1 decode variant of the fused linear (M == 1): TMA-staged packed weights, PDL
- * prefetch, warp-synchronous mma.sync contraction from registers, persistent CTAs that own
- * 16-row blocks over the full K (no cross-CTA reduction, deterministic).  Same argument
- * block as b2l_q4_linear_tc (ldx/ldy/ldres unused; split_k > 0 overrides the grid size);
- * qw_tiled must come from b2l_q4_tile_mma: [N/16 row blocks][K/64 k blocks][32 lanes][16 B].
- * For B2L_EPI_SWIGLU the rows of a 16-row block are [8 of c_fc1 | 8 of c_fc2]. */
-size_t b2l_q4_tiled_mma_bytes(int N, int K);
-int b2l_q4_tile_mma(const void* qw, void* qw_tiled, int N, int K, b2l_stream_t stream);
-int b2l_q4_untile_mma(const void* qw_tiled, void* qw, int N, int K, b2l_stream_t stream);
+/* Batch-1 decode variant of the fused linear (M == 1): TMA-staged packed weights, PDL prefetch, persistent CTAs
+ * that own 16-row blocks over the full K (no cross-CTA reduction), and an EXACT integer contraction on the legacy
+ * tensor pipe: the activation row is scaled by a power of two and split into balanced base-256 digits, digit plane j
+ * is column j of mma.sync.m16n8k32 (u8 x s8 -> s32), a packed byte feeds two weight rows (csrc/q4_gemv.cu).
+ * Same argument block as b2l_q4_linear_tc (ldx/ldy/ldres unused; split_k > 0 overrides the grid size);
+ * qw_tiled must come from b2l_q4_tile_i8: [N/16 row blocks][K/64 k blocks][32 lanes][16 B], byte = level of row g
+ * (low nibble) and of row g + 8 (high nibble).  For B2L_EPI_SWIGLU the rows of a 16-row block are
+ * [8 of c_fc1 | 8 of c_fc2].  K % 64 == 0, K <= 24576. */
+size_t b2l_q4_tiled_i8_bytes(int N, int K);
+int b2l_q4_tile_i8(const void* qw, void* qw_tiled, int N, int K, b2l_stream_t stream);
+int b2l_q4_untile_i8(const void* qw_tiled, void* qw, int N, int K, b2l_stream_t stream);
 int b2l_q4_gemv(const b2l_q4_linear_args* args, b2l_stream_t stream);
 
-/* The same fused linear for 1..8 activation rows (batched decode), same weight tiling (b2l_q4_tile_mma) and
- * argument block as b2l_q4_gemv plus `workspace`; x [M, K] with leading dimension ldx (ldx % 8 == 0), y / res
+/* The same fused linear for 1..8 activation rows (batched decode) on mma.sync.m16n8k16 (f16), weight tiling
+ * b2l_q4_tile_mma ([N/16 row blocks][K/64 k blocks][32 lanes][16 B] in m16n8k16 A-fragment order), argument block of
+ * b2l_q4_gemv plus `workspace`; x [M, K] with leading dimension ldx (ldx % 8 == 0), y / res
  * with ldy / ldres.  An mma.m16n8k16 tile has 8 columns: activation row n is column n, so 8 rows cost the MMAs
  * of one.  Two launches: the rows are normalised and converted to MMA fragment order once
  * (q4_batch_prep_kernel), then streamed stage by stage next to the weights (q4_gemv_batch_kernel).
  * Replaces the same reference code as b2l_q4_gemv for B > 1 (model.py:76-122 accepts any batch). */
 size_t b2l_q4_gemv_batch_workspace_bytes(int K);
+size_t b2l_q4_tiled_mma_bytes(int N, int K);
+int b2l_q4_tile_mma(const void* qw, void* qw_tiled, int N, int K, b2l_stream_t stream);
+int b2l_q4_untile_mma(const void* qw_tiled, void* qw, int N, int K, b2l_stream_t stream);
 int b2l_q4_gemv_batch(const b2l_q4_linear_args* args, b2l_stream_t stream);
 
 /* ------------------------------------------------------------------------------
@@ -240,7 +246,8 @@ int b2l_kv_unroll(const void* cache, const int32_t* ring_start, void* out, int B
  * ---------------------------------------------------------------------------- */
 typedef struct b2l_q4_weight {
   const void* qw_tiled;   /* b2l_q4_tile layout (tcgen05 kernel), used when B > 1; may be NULL if B == 1 */
-  const void* qw_mma;     /* b2l_q4_tile_mma layout (batch-1 kernel), used when B == 1; may be NULL if B > 1 */
+  const void* qw_mma;     /* mma.sync kernels: b2l_q4_tile_i8 layout when B == 1 (b2l_q4_gemv), b2l_q4_tile_mma
+                             layout when B in 2..8 (b2l_q4_gemv_batch); may be NULL if B > 8 */
   const void* scales;
   const void* zeros;
   int N, K;
@@ -291,10 +298,6 @@ typedef struct b2l_decode_args {
 int b2l_decode_step(const b2l_decode_args* args, b2l_stream_t stream);
 /* Number of kernels one b2l_decode_step enqueues (for bench.py's gpu_launches). */
 int b2l_decode_step_launches(const b2l_decode_args* args);
-
-/* Debug only (tools/diag.py cta_times): per-CTA stamps of the last b2l_q4_gemv launch that had a trace buffer
- * attached.  out: device uint64[n_cta][4] = {activations ready (ns), main loop done (ns), SM id, stages}. */
-int b2l_debug_gemv_cta_times(void* out, int n_cta, b2l_stream_t stream);
 
 #ifdef __cplusplus
 }

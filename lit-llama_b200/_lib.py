@@ -68,6 +68,9 @@ _SIGS = {
     "b2l_q4_tiled_mma_bytes": (c_size_t, [c_int, c_int]),
     "b2l_q4_tile_mma": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b2l_q4_untile_mma": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "b2l_q4_tiled_i8_bytes": (c_size_t, [c_int, c_int]),
+    "b2l_q4_tile_i8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "b2l_q4_untile_i8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b2l_q4_gemv": (c_int, [C.POINTER(Q4LinearArgs), c_void_p]),
     "b2l_q4_gemv_batch": (c_int, [C.POINTER(Q4LinearArgs), c_void_p]),
     "b2l_q4_gemv_batch_workspace_bytes": (c_size_t, [c_int]),
@@ -89,7 +92,6 @@ _SIGS = {
     "b2l_kv_unroll": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2l_decode_step": (c_int, [C.POINTER(DecodeArgs), c_void_p]),
     "b2l_decode_step_launches": (c_int, [C.POINTER(DecodeArgs)]),
-    "b2l_debug_gemv_cta_times": (c_int, [c_void_p, c_int, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)

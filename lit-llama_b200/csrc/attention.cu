@@ -226,7 +226,7 @@ constexpr int FD_TILE_BYTES = FD_CHUNK * 128 * 2;
 constexpr int FD_SMEM_BYTES = 2 * FD_TILE_BYTES + FD_WARPS * 128 * 4 + 2 * FD_WARPS * 4 + 16;
 
 __global__ void __launch_bounds__(FD_WARPS * 32)
-    attn_decode_fused_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ k_cache,
+    attn_decode_fused_kernel(const __nv_bfloat16* qkv, __nv_bfloat16* __restrict__ k_cache,
                              __nv_bfloat16* __restrict__ v_cache, const float* __restrict__ rope,
                              const int64_t* __restrict__ input_pos, const int32_t* __restrict__ ring_start,
                              __nv_bfloat16* __restrict__ y, float* __restrict__ work, int* __restrict__ tickets,
@@ -304,8 +304,9 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   float q[16];
   {
     float raw[16];
-    bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow), raw);
-    bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + 8), raw + 8);
+    // qkv is the output of the kernel this one was launched behind (PDL): coherent loads only
+    bf16x8_to_f32(ld_coherent_u4(qrow), raw);
+    bf16x8_to_f32(ld_coherent_u4(qrow + 8), raw + 8);
     const float scale = rsqrtf((float)HS);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -320,8 +321,8 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   if (w_slot >= j0 && w_slot < j1 && warp == 0 && grp == 0) {
     int phys = w_slot + ring; if (phys >= S) phys -= S;
     float raw[16];
-    bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + C), raw);
-    bf16x8_to_f32(*reinterpret_cast<const uint4*>(qrow + C + 8), raw + 8);
+    bf16x8_to_f32(ld_coherent_u4(qrow + C), raw);
+    bf16x8_to_f32(ld_coherent_u4(qrow + C + 8), raw + 8);
     uint32_t out[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -331,8 +332,7 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
       out[i] = (__float_as_uint(rbf(e)) >> 16) | (__float_as_uint(rbf(o)) & 0xffff0000u);
     }
     const uint4 ka = make_uint4(out[0], out[1], out[2], out[3]), kb2 = make_uint4(out[4], out[5], out[6], out[7]);
-    const uint4* vs = reinterpret_cast<const uint4*>(qrow + 2 * C);
-    const uint4 va = vs[0], vb = vs[1];
+    const uint4 va = ld_coherent_u4(qrow + 2 * C), vb = ld_coherent_u4(qrow + 2 * C + 8);
     uint4* kd = reinterpret_cast<uint4*>(k_cache + head_base + (size_t)phys * HS + d0);
     uint4* vd = reinterpret_cast<uint4*>(v_cache + head_base + (size_t)phys * HS + d0);
     kd[0] = ka; kd[1] = kb2; vd[0] = va; vd[1] = vb;

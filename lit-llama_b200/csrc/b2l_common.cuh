@@ -119,6 +119,15 @@ __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// Coherent 16-byte global load (ld.global, never ld.global.nc).  Mandatory for data written by the PREVIOUS kernel
+// when this kernel runs under programmatic dependent launch: griddepcontrol.wait orders coherent loads only, and a
+// `const __restrict__` pointer lets the compiler pick the non-coherent path (LDG.E.CONSTANT).
+__device__ __forceinline__ uint4 ld_coherent_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 // RMSNorm with the reference's bf16 rounding points (model.py:270-277, no upcast):
 //   ms = bf16(mean(bf16(x*x)));  r = bf16(rsqrt(bf16(ms + eps)));  y = bf16(scale * bf16(x * r))
 // `sumsq` is the fp32 sum over the row of bf16-rounded squares.

@@ -1,4 +1,4 @@
-// Batch-1 decode kernel: fused [RMSNorm ->] int4 weight-only GEMV [-> residual | SwiGLU].
+// Batch-1 decode kernel: fused [RMSNorm ->] int4 weight-only GEMV [-> residual | SwiGLU], integer tensor pipe.
 //
 // Replaces, for gptq.int4 with one (scale, zero) per output row and a single activation row:
 //   ColBlockQuantizedLinear.forward      lit_llama/quantization.py:413-423
@@ -6,29 +6,36 @@
 //   RMSNorm.forward                      lit_llama/model.py:270-277      (prologue)
 //   x + h / silu(a) * b                  lit_llama/model.py:166-167, 252 (epilogue)
 //
-// Why not tcgen05 here: measured on B200 (tools/diag.py mma_rate / trace)
-// a single thread issues a 128x16x16 tcgen05.mma every 45-80 cycles and every
-// convert -> commit -> mbarrier round trip costs 300-500 cycles, so at one activation row the
-// tensor-memory path is latency-bound at ~1/5 of HBM speed.  This kernel keeps the
-// Blackwell data movement (TMA bulk copies into an mbarrier ring, PDL prefetch of the weights
-// ahead of the dependency) and runs the tiny contraction warp-synchronously with
-// mma.sync.m16n8k16 from registers: no TMEM hand-offs, no cross-CTA reduction.
+// The contraction y[o] = scale[o] * sum_k (level[o,k] - zero[o]) * x[k] is evaluated in EXACT integer arithmetic:
+//   * the activation row (after the RMSNorm prologue, i.e. the bf16 values the reference feeds its linear) is
+//     scaled by a power of two 2^sh chosen from max|x| and rounded to X[k] (|X| < 2^30 with four digits, 2^22 with
+//     three), then split into balanced base-256 digits X = sum_j d_j 256^j, d_j in [-128, 127];
+//   * mma.sync.m16n8k32 (u8 x s8 -> s32, SASS IMMA.16832.U8.S8) has 8 result columns and a single activation row
+//     needs one: digit plane j is column j, so all digits cost ONE MMA per 16 x 32 weight tile;
+//   * a packed byte holds two levels.  It is fed to the tensor core UNMASKED as the operand of row g (value
+//     level[g] + 16 level[g+8]) and with the low nibbles masked off as the operand of row g + 8 (16 level[g+8]):
+//     one LOP3 per word, and the epilogue recovers row g = D[g] - D[g+8], row g + 8 = D[g+8] / 16;
+//   * int32 accumulators cannot overflow for K <= 65536 (255 * 127 * K < 2^31); digits are recombined in int64 and
+//     the zero point is removed with the exact sum of X: y = scale * 2^-sh * (sum level X - zero * sum X).
+// Measured on B200 (tools/diag.py imma_rate / hmma_rate, profiles/r02_micro_imma_rate.txt): IMMA.16832 issues every
+// 8.1 cycles per SM sub-partition like HMMA.16816, but consumes 512 levels behind 2 LOP3 where the f16 form consumed
+// 256 behind 5 ALU ops: 10-12 issue cycles per 512 levels instead of 30.  Results no longer depend on the order of
+// the K split, carry no 1024-bias cancellation, and have no fp16 range limit on the activations.
 //
-// Work split: a persistent CTA owns 16-row blocks rb = cta, cta + grid, ... over the FULL K
-// (so nothing is reduced across CTAs and the result is deterministic).  The 8 consumer warps
-// split K inside a stage; their fp32 partials meet in shared memory, where the epilogue warp
-// applies y = scale * (acc - (1024 + zero) * sum_lo(x) - (64 + zero) * sum_hi(x)) and the fused epilogue.
+// Why not tcgen05 here: one thread issues a 128x16x16 tcgen05.mma every ~55 cycles (4 issuing warps: 15 cycles,
+// profiles/r02_micro_issuers_gridflag.txt), but its A operand must first be expanded to 16-bit lanes by the same
+// ALUs (>= 4 LOP3 per packed word) and handed over through tensor memory (300-500 cycles per hand-off, DESIGN.md
+// section 3); the IMMA form needs 1 LOP3 per packed word and no hand-off.  tcgen05 carries the M > 8 shapes.
 //
-// Weight layout (b2l_q4_tile_mma): [N/16 row blocks][K/64 k blocks][32 lanes][16 B].  Word c of
-// lane (g = lane/4, t = lane%4) holds the A fragment of k16 chunk c: nibble s (s < 4) is row
-// g + 8*(s>>1), k = 64*kb + 16*c + 2*t + 8*(s&1); nibble s+4 is the same row at k+1.  The A
-// registers of mma.m16n8k16 are built as fp16 pairs with one shift per word:
-//   a0 = (w      & 0x000f000f) | 0x64006400   = 1024 + level       (row g,   k lower half)
-//   a2 = (w      & 0x00f000f0) | 0x64006400   = 1024 + 16 * level  (row g,   k upper half)
-//   a1, a3 = the same two masks on w >> 8                          (row g+8)
-// and the activations of the upper half are fed as x / 16 (exact in fp16), so the accumulator holds
-// sum(level * x) + 1024 * sum_lo(x) + 64 * sum_hi(x); the two sums are removed with the zero point.
-// bf16 -> fp16 of the activations is exact inside the fp16 normal range; |x| > 65504 saturates.
+// Data movement is unchanged from round 1: a persistent CTA owns 16-row blocks over the FULL K, a producer warp
+// streams 16 KB stages with TMA bulk copies into an mbarrier ring (issued before griddepcontrol.wait, so the
+// weights of this linear stream while the previous kernel drains), 8 consumer warps split K inside a stage.
+//
+// Weight layout (b2l_q4_tile_i8): [N/16 row blocks][K/64 k blocks][32 lanes][16 B].  Lane (g = lane/4, t = lane%4),
+// word 2c + j (c = k32 chunk of the k block, j = 0/1), byte i: low nibble = level[16 rb + g][k], high nibble =
+// level[16 rb + g + 8][k], k = 64 kb + 32 c + 8 t + 4 j + i.  (The k order inside a chunk is a free choice as long as
+// the activation digits use the same one; this one gives every prologue thread, which owns 8 consecutive k, both
+// B registers of one lane.)
 #include <cstdlib>
 
 #include "q4_mma_common.cuh"
@@ -50,33 +57,47 @@ struct Params {
   int nocompute;           // debug: consumers release every stage untouched (pure TMA streaming rate)
 };
 
-// debug (tools/diag.py cta_times, only written when a trace buffer is attached): per CTA
-// {x_ready ns, loop_done ns, %smid, stages streamed}
-__device__ unsigned long long g_cta_dbg[1024 * 4];
+// digit-plane stride in bytes: one byte per k, padded so that planes n and n + 1 fall into different bank halves
+__host__ __device__ inline uint32_t plane_stride(int K) { return (uint32_t)K + ((K % 128 == 0) ? 64u : 0u); }
 
 // shared memory map
 struct SmemLayout {
-  uint32_t ring, xf, scratch, red, bars, total;
+  uint32_t ring, xf, zero, scratch, red, bars, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int nst, int K) {
+__host__ __device__ inline SmemLayout smem_layout(int nst, int K, int ndig) {
   SmemLayout L;
   uint32_t o = 0;
   L.ring = o;    o += (uint32_t)nst * STAGE_BYTES;
-  L.xf = o;      o += (uint32_t)(K / KB) * 128;       // B fragments: [k block][t (4)][32 B]
-  L.scratch = o; o += 2 * NCW * RB * MAX_HALVES * 4;  // [buf][warp][half][row] fp32 partials
-  L.red = o;     o += 128;                            // per-warp reduction scratch: sum of squares, sum(x) of either k class
-  o = (o + 7u) & ~7u;
+  L.xf = o;      o += (uint32_t)ndig * plane_stride(K);   // digit planes: [digit][k block][t (4)][16 B]
+  L.zero = o;    o += 16;                                 // the B operand of the unused MMA columns
+  L.scratch = o; o += 2 * NCW * MAX_HALVES * RB * 16;     // [buf][warp][half][row][digit (4)] int32 partials
+  L.red = o;     o += 192;                                // reductions: float[8] sumsq, float[8] max, int64[8] sum X, int sh
   L.bars = o;    o += 2 * MAX_STAGES * 8;
   L.total = (o + 127u) & ~127u;
   return L;
 }
 
+// X (|X| < 2^30) -> word whose bytes are its balanced base-256 digits (byte 3 = signed top digit)
+__device__ __forceinline__ uint32_t balanced_digits(int X) { return ((uint32_t)X + 0x00808080u) ^ 0x00808080u; }
+
+// One k-block position (64 k = two k32 chunks) of NH 16-row halves: LDS.128 per half, 1 LOP3 + 1 IMMA per packed word pair.
+template <int NH>
+__device__ __forceinline__ void kblock_imma(int (&acc)[MAX_HALVES][2][4], const uint8_t* wbase, const uint4& xb) {
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const uint4 wv = *reinterpret_cast<const uint4*>(wbase + h * HALF_STAGE_BYTES);
+    mma_u8s8_16832(acc[h][0], wv.x, wv.x & 0xf0f0f0f0u, wv.y, wv.y & 0xf0f0f0f0u, xb.x, xb.y);
+    mma_u8s8_16832(acc[h][1], wv.z, wv.z & 0xf0f0f0f0u, wv.w, wv.w & 0xf0f0f0f0u, xb.z, xb.w);
+  }
+}
+
 // MAXC = activation chunks (2048 elements each) a thread block caches in registers during the prologue:
 // 6 covers K <= 12288 (every 7B/13B/30B layer), 12 covers K <= 24576 (65B mlp.c_proj, K = 22016).
-template <int MAXC>
+// NDIG = base-256 digits of the scaled activations: 4 (|X| < 2^30) or 3 (|X| < 2^22; wide K, smaller planes).
+template <int MAXC, int NDIG>
 __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const SmemLayout L = smem_layout(p.nst, p.K);
+  const SmemLayout L = smem_layout(p.nst, p.K, NDIG);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_kb = p.K / KB;                                              // k blocks per 16-row block
@@ -87,6 +108,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
   const int n_units = (rb_hi - rb_lo + 1) / 2;
   const int total_stages = n_units * stages_per_unit;
   const uint32_t bar_full = sbase + L.bars, bar_empty = bar_full + MAX_STAGES * 8;
+  const uint32_t PS = plane_stride(p.K);
 
   if (tid == 0) tl_min(p.tl, 0);
   if (tid == 0) {
@@ -96,6 +118,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < 4) reinterpret_cast<uint32_t*>(smem + L.zero)[tid] = 0u;
   __syncthreads();
 
   if (warp == PRODUCER_WARP) {
@@ -116,7 +139,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
           for (int h = 0; h < halves; ++h)
             tma_bulk_g2s(sbase + L.ring + slot * STAGE_BYTES + h * HALF_STAGE_BYTES,
                          src + ((size_t)h * n_kb + (size_t)s * KBP_PER_STAGE) * KB_BYTES, bytes, bar_full + slot * 8);
-          if (p.tl != nullptr && blockIdx.x == 0 && it < 12) p.tl[40 + it] = globaltimer_ns();
           if (++slot == p.nst) { slot = 0; phase ^= 1; }
           if (it + 1 == min(total_stages, p.nst)) pdl_launch_dependents();  // ring full: next kernel may prefetch
         }
@@ -125,8 +147,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
     }
   } else if (warp < NCW) {
     // ===================== consumer warps =====================
-    float* red = reinterpret_cast<float*>(smem + L.red);  // [0..7] sum of squares, [8..15] sum of x, per warp
-    // ---- activations: [RMSNorm], B-fragment order, sum(x)
+    float* red = reinterpret_cast<float*>(smem + L.red);   // [0..7] sum of squares, [8..15] max, then int64[8] sum X, int sh
+    long long* red_sx = reinterpret_cast<long long*>(smem + L.red + 64);
+    int* red_sh = reinterpret_cast<int*>(smem + L.red + 128);
+    // ---- activations: [RMSNorm], power-of-two scaling, balanced digits in B-fragment order, exact sum(X)
     {
       const bool norm = (p.prologue == B2L_PRO_RMSNORM);
       constexpr int NT = NCW * 32;   // 256 threads, 8 elements each per pass
@@ -141,48 +165,57 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
       }
       pdl_wait();
       if (tid == 0) tl_max(p.tl, 1);
+      // written by the previous kernel: coherent loads (p.x is neither const __restrict__ nor read through ld.global.nc)
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         const int k = (c * NT + tid) * 8;
         xv[c] = make_uint4(0, 0, 0, 0);
-        if (k < p.K) xv[c] = *reinterpret_cast<const uint4*>(p.x + k);
+        if (k < p.K) xv[c] = ld_coherent_u4(p.x + k);
       }
       const int nchunk = (p.K + NT * 8 - 1) / (NT * 8);  // warp-uniform: chunks that hold data
-      float rinv = 1.f;
-      if (p.tl != nullptr) {  // debug: when did the activation loads land?
-        uint32_t sink = 0;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) sink |= xv[c].x;
-        if (tid == 0 && sink != 0x12345678u) tl_max(p.tl, 5);
-      }
+      // pass 1: sum of bf16-rounded squares (RMSNorm, model.py:274) and max |x * scale| (bounds the normalised values)
       // bf16x2 arithmetic: one HMUL2 is the exactly-rounded bf16 product the reference computes
-      // (bf16 * bf16 is exact in fp32, so rounding the fp32 product once == the packed multiply)
-      if (norm) {
-        float ss = 0.f;
+      float ss = 0.f, mx = 0.f;
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-          if (c < nchunk) {
-            const uint32_t w[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < nchunk) {
+          const uint32_t w[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+          const uint32_t g[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 4; ++q) {
+            const float lo = __uint_as_float(w[q] << 16), hi = __uint_as_float(w[q] & 0xffff0000u);
+            if (norm) {
               const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
               const __nv_bfloat162 sq = __hmul2(v, v);
               const uint32_t su = *reinterpret_cast<const uint32_t*>(&sq);
               ss += __uint_as_float(su << 16) + __uint_as_float(su & 0xffff0000u);
+              const float glo = __uint_as_float(g[q] << 16), ghi = __uint_as_float(g[q] & 0xffff0000u);
+              mx = fmaxf(mx, fmaxf(fabsf(lo * glo), fabsf(hi * ghi)));
+            } else {
+              mx = fmaxf(mx, fmaxf(fabsf(lo), fabsf(hi)));
             }
           }
         }
-        ss = warp_sum(ss);
-        if (lane == 0) red[warp] = ss;
-        named_bar_sync(1, NT);
-        if (tid == 0) tl_max(p.tl, 6);
-        ss = 0.f;
-#pragma unroll
-        for (int w = 0; w < NCW; ++w) ss += red[w];
-        rinv = rms_rinv(ss, p.K, p.eps);
       }
+      ss = warp_sum(ss);
+      mx = warp_max(mx);
+      if (lane == 0) { red[warp] = ss; red[8 + warp] = mx; }
+      named_bar_sync(1, NT);
+      ss = 0.f; mx = 0.f;
+#pragma unroll
+      for (int w = 0; w < NCW; ++w) { ss += red[w]; mx = fmaxf(mx, red[8 + w]); }
+      float rinv = 1.f;
+      if (norm) {
+        rinv = rms_rinv(ss, p.K, p.eps);
+        mx = mx * rinv * 1.01f;     // |bf16(g * bf16(x * rinv))| <= |g x| rinv (1 + 2^-8)^2
+      }
+      // 2^sh: the largest power of two with max|v| * 2^sh < 2^(8 NDIG - 2)
+      const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;   // mx < 2^(e + 1)
+      int sh = (8 * NDIG - 3) - e;
+      sh = max(-126, min(126, sh));
+      const float scale = __uint_as_float((uint32_t)(sh + 127) << 23);
       const __nv_bfloat162 rinv2 = __float2bfloat162_rn(rinv);  // rinv is already a bf16 value
-      float sx = 0.f;
+      long long sx = 0;
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         const int k = (c * NT + tid) * 8;
@@ -198,62 +231,62 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
               w[q] = *reinterpret_cast<const uint32_t*>(&y2);
             }
           }
-          // 8 consecutive k = half of a k16 chunk: pair q (k = k0 + 2q, +1) is B register (half) of lane t = q
-          // xf[k block][t][chunk c16 (4)][half (2)] u32.  The half is (tid & 1): a thread only ever sees one k class.
-          // The tensor-core operand is fp16 (exact for a bf16 value in the fp16 range); the upper half of every
-          // k16 chunk is pre-divided by 16 because its weights are unpacked as 1024 + 16*level (see the main loop).
-          const int kb = k >> 6, c16 = (k >> 4) & 3, half = (k >> 3) & 1;
-          const float pre = half ? 0.0625f : 1.0f;
-          uint32_t* dst = reinterpret_cast<uint32_t*>(smem + L.xf + kb * 128);
+          uint32_t xd[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float lo = __uint_as_float(w[q] << 16), hi = __uint_as_float(w[q] & 0xffff0000u);
-            sx += lo + hi;
-            dst[q * 8 + c16 * 2 + half] = pack_f16x2(lo * pre, hi * pre);
+            const int X0 = __float2int_rn(__uint_as_float(w[q] << 16) * scale);          // exact product: power-of-two scale
+            const int X1 = __float2int_rn(__uint_as_float(w[q] & 0xffff0000u) * scale);
+            sx += (long long)X0 + (long long)X1;
+            xd[2 * q] = balanced_digits(X0);
+            xd[2 * q + 1] = balanced_digits(X1);
           }
-        }
-      }
-      // even lanes hold lower-half (k % 16 < 8) sums, odd lanes upper-half sums
+          // 4 x 4 byte transposes: word (j, n) = digit n of elements 4j .. 4j+3  (B register j of lane t, column n)
+          uint32_t dj[2][4];
 #pragma unroll
-      for (int o = 16; o > 1; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
-      if (lane < 2) red[8 + 8 * lane + warp] = sx;   // the epilogue warp adds the 8 partials of each class in a fixed order
-      named_bar_sync(3, NT + 32);          // releases the epilogue warp too: xf and the partial sums are ready
-      if (tid == 0) {
-        tl_max(p.tl, 2);
-        if (p.tl != nullptr) {
-          atomicMin(p.tl + 60, globaltimer_ns());
-          if (blockIdx.x < 1024) g_cta_dbg[blockIdx.x * 4] = globaltimer_ns();
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t lo01 = __byte_perm(xd[4 * j], xd[4 * j + 1], 0x5140), hi01 = __byte_perm(xd[4 * j], xd[4 * j + 1], 0x7362);
+            const uint32_t lo23 = __byte_perm(xd[4 * j + 2], xd[4 * j + 3], 0x5140), hi23 = __byte_perm(xd[4 * j + 2], xd[4 * j + 3], 0x7362);
+            dj[j][0] = __byte_perm(lo01, lo23, 0x5410);
+            dj[j][1] = __byte_perm(lo01, lo23, 0x7632);
+            dj[j][2] = __byte_perm(hi01, hi23, 0x5410);
+            dj[j][3] = __byte_perm(hi01, hi23, 0x7632);
+          }
+          // k = 64 kb + 32 c32 + 8 t + (0..7): plane n, k block kb, lane slot t, words 2 c32, 2 c32 + 1
+          uint8_t* dst = smem + L.xf + (k >> 6) * 64 + ((k >> 3) & 3) * 16 + ((k >> 5) & 1) * 8;
+#pragma unroll
+          for (int n = 0; n < NDIG; ++n) *reinterpret_cast<uint2*>(dst + n * PS) = make_uint2(dj[0][n], dj[1][n]);
         }
       }
+      // exact sum of X over the row: int64 warp reduction, fixed-order sum of the 8 warp partials in the epilogue
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      if (lane == 0) red_sx[warp] = sx;
+      if (tid == 0) *red_sh = sh;
+      named_bar_sync(3, NT + 32);          // releases the epilogue warp too: digit planes, sum X and sh are ready
+      if (tid == 0) tl_max(p.tl, 2);
     }
 
     // ---- weights: stage -> registers -> mma.sync.  Warp w takes k-block positions w and w + 8 of a stage
     // and, for each, both 16-row halves of the unit (the B fragments are loaded once per position).
-    const int t4 = lane & 3;
-    // fp16 unpack: (w & 0x000f000f) | 0x64006400 = (1024 + level) pairs, (w & 0x00f000f0) | 0x64006400 =
-    // (1024 + 16 * level) pairs -- two of the four A registers of a k16 chunk need no shift at all
-    uint32_t kmask, kmask4, kmagic;
-    asm volatile("mov.b32 %0, 0x000f000f;" : "=r"(kmask));
-    asm volatile("mov.b32 %0, 0x00f000f0;" : "=r"(kmask4));
-    asm volatile("mov.b32 %0, 0x64006400;" : "=r"(kmagic));
+    // lanes 0..15 = MMA columns 0..3 = digit planes; lanes 16..31 (columns 4..7) read the zero block
+    const int ncol = lane >> 2, t4 = lane & 3;
+    const uint8_t* xf_lane = (ncol < NDIG) ? smem + L.xf + ncol * PS + t4 * 16 : smem + L.zero;
+    const int xf_step = (ncol < NDIG) ? 64 : 0;
     int slot = 0;
     uint32_t phase = 0;
-    float* scratch = reinterpret_cast<float*>(smem + L.scratch);
-    const uint8_t* xf_lane = smem + L.xf + t4 * 32;
-    int dbg_it = 0;
+    int* scratch = reinterpret_cast<int*>(smem + L.scratch);
     for (int u = 0; u < n_units; ++u) {
       const int halves = min(2, rb_hi - (rb_lo + 2 * u));
-      float acc[MAX_HALVES][2][4];
+      int acc[MAX_HALVES][2][4];
 #pragma unroll
       for (int h = 0; h < MAX_HALVES; ++h)
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[h][c][i] = 0.f;
+          for (int i = 0; i < 4; ++i) acc[h][c][i] = 0;
       for (int s = 0; s < stages_per_unit; ++s) {
         const int nkb = min(KBP_PER_STAGE, n_kb - s * KBP_PER_STAGE);
         mbar_wait(bar_full + slot * 8, phase);
-        if (p.tl != nullptr && blockIdx.x == 0 && tid == 0 && dbg_it < 12) p.tl[8 + 2 * dbg_it] = globaltimer_ns();
         const uint8_t* st_base = smem + L.ring + slot * STAGE_BYTES + lane * 16;
         if (nkb == KBP_PER_STAGE && !p.nocompute) {
           // the common case (full stage), branch-free for two halves and for one
@@ -261,15 +294,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
 #pragma unroll
             for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
               const int kbl = i * NCW + warp;
-              const uint4* xp = reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * 128);
-              kblock_mma<MAX_HALVES>(acc, st_base + kbl * KB_BYTES, xp[0], xp[1], kmask, kmask4, kmagic);
+              const uint4 xb = *reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * xf_step);
+              kblock_imma<MAX_HALVES>(acc, st_base + kbl * KB_BYTES, xb);
             }
           } else {
 #pragma unroll
             for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
               const int kbl = i * NCW + warp;
-              const uint4* xp = reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * 128);
-              kblock_mma<1>(acc, st_base + kbl * KB_BYTES, xp[0], xp[1], kmask, kmask4, kmagic);
+              const uint4 xb = *reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * xf_step);
+              kblock_imma<1>(acc, st_base + kbl * KB_BYTES, xb);
             }
           }
         } else if (!p.nocompute) {
@@ -277,55 +310,47 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
           for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
             const int kbl = i * NCW + warp;  // k-block position inside the stage
             if (kbl < nkb) {
-              const uint4* xp = reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * 128);
-              if (halves == MAX_HALVES) kblock_mma<MAX_HALVES>(acc, st_base + kbl * KB_BYTES, xp[0], xp[1], kmask, kmask4, kmagic);
-              else kblock_mma<1>(acc, st_base + kbl * KB_BYTES, xp[0], xp[1], kmask, kmask4, kmagic);
+              const uint4 xb = *reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * xf_step);
+              if (halves == MAX_HALVES) kblock_imma<MAX_HALVES>(acc, st_base + kbl * KB_BYTES, xb);
+              else kblock_imma<1>(acc, st_base + kbl * KB_BYTES, xb);
             }
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + slot * 8);
-        if (p.tl != nullptr && blockIdx.x == 0 && tid == 0 && dbg_it < 12) p.tl[9 + 2 * dbg_it] = globaltimer_ns();
-        ++dbg_it;
         if (++slot == p.nst) { slot = 0; phase ^= 1; }
       }
-      // column 0 of each 16x8 result: lanes with t == 0 hold rows g (acc[.][0]) and g + 8 (acc[.][2])
+      // 16 x 8 result: lane (g, t) holds rows g (c0, c1) and g + 8 (c2, c3) of columns 2t, 2t + 1 = digits 2t, 2t + 1.
+      // row g = D[g] - D[g+8] (the unmasked byte carried 16 * level[g+8] as well), row g + 8 = D[g+8] / 16 (exact)
       const int buf = u & 1;
       named_bar_sync(4 + buf, NCW * 32 + 32);  // the epilogue warp has drained this scratch buffer (two units ago)
-      if (t4 == 0) {
+      if (t4 < 2) {
 #pragma unroll
         for (int h = 0; h < MAX_HALVES; ++h) {
-          float* dst = scratch + ((buf * NCW + warp) * MAX_HALVES + h) * RB + (lane >> 2);
-          dst[0] = acc[h][0][0] + acc[h][1][0];
-          dst[8] = acc[h][0][2] + acc[h][1][2];
+          const int c0 = acc[h][0][0] + acc[h][1][0], c1 = acc[h][0][1] + acc[h][1][1];
+          const int c2 = acc[h][0][2] + acc[h][1][2], c3 = acc[h][0][3] + acc[h][1][3];
+          int* dst = scratch + (((buf * NCW + warp) * MAX_HALVES + h) * RB + (lane >> 2)) * 4 + 2 * t4;
+          *reinterpret_cast<int2*>(dst) = make_int2(c0 - c2, c1 - c3);
+          *reinterpret_cast<int2*>(dst + 8 * 4) = make_int2(c2 >> 4, c3 >> 4);
         }
       }
       __syncwarp();
       named_bar_arrive(6 + buf, NCW * 32 + 32);  // partials of this unit are in the scratch buffer
     }
-    if (tid == 0) {
-      tl_max(p.tl, 3);
-      if (p.tl != nullptr) {
-        atomicMin(p.tl + 61, globaltimer_ns());
-        if (blockIdx.x < 1024) {
-          uint32_t smid;
-          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-          g_cta_dbg[blockIdx.x * 4 + 1] = globaltimer_ns();
-          g_cta_dbg[blockIdx.x * 4 + 2] = smid;
-          g_cta_dbg[blockIdx.x * 4 + 3] = (unsigned long long)total_stages;
-        }
-      }
-    }
+    if (tid == 0) tl_max(p.tl, 3);
   } else {
     // ===================== epilogue warp: lane = row of the 32-row unit =====================
     pdl_wait();
-    const float* red = reinterpret_cast<const float*>(smem + L.red);
-    const float* scratch = reinterpret_cast<const float*>(smem + L.scratch);
+    const long long* red_sx = reinterpret_cast<const long long*>(smem + L.red + 64);
+    const int* red_sh = reinterpret_cast<const int*>(smem + L.red + 128);
+    const int* scratch = reinterpret_cast<const int*>(smem + L.scratch);
     named_bar_sync(3, NCW * 32 + 32);
-    // sum of the (normalised) activations over the lower (k % 16 < 8) and upper halves of the k16 chunks
-    float sum_lo = 0.f, sum_hi = 0.f;
+    long long sum_x = 0;
 #pragma unroll
-    for (int w = 0; w < NCW; ++w) { sum_lo += red[8 + w]; sum_hi += red[16 + w]; }
+    for (int w = 0; w < NCW; ++w) sum_x += red_sx[w];
+    const double dsum_x = (double)sum_x;
+    const int sh = *red_sh;
+    const double inv_scale = __longlong_as_double((long long)(1023 - sh) << 52);   // 2^-sh
     // both scratch buffers start free
     if (n_units > 0) named_bar_arrive(4, NCW * 32 + 32);
     if (n_units > 1) named_bar_arrive(5, NCW * 32 + 32);
@@ -342,12 +367,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
       float resv = 0.f;
       if (p.epilogue == B2L_EPI_RESIDUAL && active && orow < p.N) resv = bf2f(p.res[orow]);
       named_bar_sync(6 + buf, NCW * 32 + 32);
-      float t = 0.f;
+      int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 #pragma unroll
-      for (int w = 0; w < NCW; ++w) t += scratch[((buf * NCW + w) * MAX_HALVES + half) * RB + row];  // fixed order: deterministic
+      for (int w = 0; w < NCW; ++w) {   // integer sums: exact, independent of the order
+        const int4 v = *reinterpret_cast<const int4*>(scratch + (((buf * NCW + w) * MAX_HALVES + half) * RB + row) * 4);
+        d0 += v.x; d1 += v.y; d2 += v.z; d3 += v.w;
+      }
       if (u + 2 < n_units) named_bar_arrive(4 + buf, NCW * 32 + 32);                                   // scratch buffer free again
-      // t = sum q x + 1024 sum_lo + 64 sum_hi  (upper half: (1024 + 16 q) * x / 16)
-      const float v = rbf(sc * ((t - (1024.0f + zero) * sum_lo) - (64.0f + zero) * sum_hi));
+      // sum_k level X = d0 + 256 d1 + 65536 d2 + 2^24 d3 (exact in int64, < 2^53)
+      const long long tq = (long long)d0 + ((long long)d1 << 8) + ((long long)d2 << 16) + ((long long)d3 << 24);
+      const float tf = (float)(((double)tq - (double)zero * dsum_x) * inv_scale);   // sum (level - zero) x, one rounding
+      const float v = rbf(sc * tf);
       if (p.epilogue == B2L_EPI_SWIGLU) {
         // rows 0..7 of a 16-row block are c_fc1[o..o+7], rows 8..15 are c_fc2[o..o+7]
         const float b = __shfl_down_sync(0xffffffffu, v, 8);
@@ -363,47 +393,48 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
   }
 }
 
-// ---------------------------------------------------------------- re-tiling for the mma.sync layout
-__global__ void q4_tile_mma_kernel(const uint8_t* __restrict__ qw, uint32_t* __restrict__ out, int N, int K) {
+// ---------------------------------------------------------------- re-tiling for the int8-MMA layout
+__global__ void q4_tile_i8_kernel(const uint8_t* __restrict__ qw, uint32_t* __restrict__ out, int N, int K) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one output word
   const int n_kb = K / KB;
   const int n_rb = (N + RB - 1) / RB;
   const size_t total = (size_t)n_rb * n_kb * 32 * 4;
   if (idx >= total) return;
-  const int c = idx & 3, lane = (idx >> 2) & 31;
+  const int wd = idx & 3, lane = (idx >> 2) & 31;
   const size_t rest = idx >> 7;
   const int kb = (int)(rest % n_kb), rb = (int)(rest / n_kb);
-  const int g = lane >> 2, t = lane & 3;
+  const int g = lane >> 2, t = lane & 3, c = wd >> 1, j = wd & 1;
   uint32_t w = 0;
 #pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const int ss = s & 3;
-    const int row = rb * RB + g + 8 * (ss >> 1);
-    const int k = kb * KB + 16 * c + 2 * t + 8 * (ss & 1) + (s >> 2);
-    if (row < N) {
-      const uint8_t b = qw[(size_t)(k >> 1) * N + row];
-      w |= (uint32_t)((b >> ((k & 1) * 4)) & 0xF) << (4 * s);
+  for (int i = 0; i < 4; ++i) {
+    const int k = kb * KB + 32 * c + 8 * t + 4 * j + i;
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int row = rb * RB + g + 8 * hi;
+      if (row < N) {
+        const uint8_t b = qw[(size_t)(k >> 1) * N + row];
+        w |= (uint32_t)((b >> ((k & 1) * 4)) & 0xF) << (8 * i + 4 * hi);
+      }
     }
   }
   out[idx] = w;
 }
 
-__global__ void q4_untile_mma_kernel(const uint32_t* __restrict__ tiled, uint8_t* __restrict__ qw, int N, int K) {
+__global__ void q4_untile_i8_kernel(const uint32_t* __restrict__ tiled, uint8_t* __restrict__ qw, int N, int K) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one packed byte [j][o]
   const size_t total = (size_t)(K / 2) * N;
   if (idx >= total) return;
-  const int o = (int)(idx % N), j = (int)(idx / N);
+  const int o = (int)(idx % N), jp = (int)(idx / N);
   const int n_kb = K / KB;
   uint8_t b = 0;
 #pragma unroll
   for (int nr = 0; nr < 2; ++nr) {
-    const int k = 2 * j + nr;
-    const int kb = k / KB, kl = k % KB, c = kl >> 4, k16 = kl & 15;
-    const int hi8 = k16 >> 3, t = (k16 & 7) >> 1, odd = k16 & 1;
-    const int rb = o / RB, rl = o % RB, g = rl & 7, r8 = rl >> 3;
-    const int s = (r8 << 1 | hi8) + 4 * odd;
-    const uint32_t w = tiled[(((size_t)rb * n_kb + kb) * 32 + (g * 4 + t)) * 4 + c];
-    b |= (uint8_t)(((w >> (4 * s)) & 0xF) << (4 * nr));
+    const int k = 2 * jp + nr;
+    const int kb = k / KB, kl = k % KB, c = kl >> 5, kk = kl & 31;
+    const int t = kk >> 3, j = (kk >> 2) & 1, i = kk & 3;
+    const int rb = o / RB, rl = o % RB, g = rl & 7, hi = rl >> 3;
+    const uint32_t w = tiled[(((size_t)rb * n_kb + kb) * 32 + (g * 4 + t)) * 4 + 2 * c + j];
+    b |= (uint8_t)(((w >> (8 * i + 4 * hi)) & 0xF) << (4 * nr));
   }
   qw[idx] = b;
 }
@@ -414,41 +445,63 @@ __global__ void q4_untile_mma_kernel(const uint32_t* __restrict__ tiled, uint8_t
 using namespace b2l;
 using namespace b2l::q4mv;
 
-extern "C" size_t b2l_q4_tiled_mma_bytes(int N, int K) {
+extern "C" size_t b2l_q4_tiled_i8_bytes(int N, int K) {
   if (N <= 0 || K <= 0 || K % KB != 0) return 0;
   return (size_t)((N + RB - 1) / RB) * (K / KB) * KB_BYTES;
 }
 
-extern "C" int b2l_q4_tile_mma(const void* qw, void* qw_tiled, int N, int K, b2l_stream_t stream) {
-  B2L_CHECK_ARG(qw && qw_tiled && N > 0 && K > 0, "b2l_q4_tile_mma: bad argument");
-  B2L_CHECK_SUPPORTED(K % KB == 0, "b2l_q4_tile_mma: in_features %d must be a multiple of %d", K, KB);
-  const size_t total = b2l_q4_tiled_mma_bytes(N, K) / 4;
-  q4_tile_mma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)qw, (uint32_t*)qw_tiled, N, K);
-  B2L_LAUNCH_CHECK("q4_tile_mma_kernel");
+extern "C" int b2l_q4_tile_i8(const void* qw, void* qw_tiled, int N, int K, b2l_stream_t stream) {
+  B2L_CHECK_ARG(qw && qw_tiled && N > 0 && K > 0, "b2l_q4_tile_i8: bad argument");
+  B2L_CHECK_SUPPORTED(K % KB == 0, "b2l_q4_tile_i8: in_features %d must be a multiple of %d", K, KB);
+  const size_t total = b2l_q4_tiled_i8_bytes(N, K) / 4;
+  q4_tile_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)qw, (uint32_t*)qw_tiled, N, K);
+  B2L_LAUNCH_CHECK("q4_tile_i8_kernel");
   return 0;
 }
 
-extern "C" int b2l_q4_untile_mma(const void* qw_tiled, void* qw, int N, int K, b2l_stream_t stream) {
-  B2L_CHECK_ARG(qw && qw_tiled && N > 0 && K > 0, "b2l_q4_untile_mma: bad argument");
-  B2L_CHECK_SUPPORTED(K % KB == 0, "b2l_q4_untile_mma: in_features %d must be a multiple of %d", K, KB);
+extern "C" int b2l_q4_untile_i8(const void* qw_tiled, void* qw, int N, int K, b2l_stream_t stream) {
+  B2L_CHECK_ARG(qw && qw_tiled && N > 0 && K > 0, "b2l_q4_untile_i8: bad argument");
+  B2L_CHECK_SUPPORTED(K % KB == 0, "b2l_q4_untile_i8: in_features %d must be a multiple of %d", K, KB);
   const size_t total = (size_t)(K / 2) * N;
-  q4_untile_mma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)qw_tiled, (uint8_t*)qw, N, K);
-  B2L_LAUNCH_CHECK("q4_untile_mma_kernel");
+  q4_untile_i8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)qw_tiled, (uint8_t*)qw, N, K);
+  B2L_LAUNCH_CHECK("q4_untile_i8_kernel");
   return 0;
 }
 
-extern "C" int b2l_debug_gemv_cta_times(void* out, int n_cta, b2l_stream_t stream) {
-  B2L_CHECK_ARG(out && n_cta > 0 && n_cta <= 1024, "b2l_debug_gemv_cta_times: bad argument");
-  B2L_CUDA(cudaMemcpyFromSymbolAsync(out, g_cta_dbg, (size_t)n_cta * 4 * sizeof(unsigned long long), 0, cudaMemcpyDeviceToDevice,
-                                     (cudaStream_t)stream));
+namespace {
+constexpr int MAX_K = 12 * NCW * 32 * 8;   // 24576
+
+template <int MAXC, int NDIG>
+int launch_gemv(const Params& p0, int ctas_per_sm, int grid_override, bool pdl, cudaStream_t stream) {
+  Params p = p0;
+  // ring: as deep as fits `ctas_per_sm` CTAs per SM
+  const uint32_t budget = (ctas_per_sm >= 2 ? 110u : 224u) * 1024u;
+  const uint32_t fixed = smem_layout(0, p.K, NDIG).total;
+  int nst = fixed + 2 * STAGE_BYTES <= budget ? (int)((budget - fixed) / STAGE_BYTES) : 0;
+  if (nst > MAX_STAGES) nst = MAX_STAGES;
+  static const int env_nst = [] { const char* e = getenv("B2L_GEMV_STAGES"); return e ? atoi(e) : 0; }();
+  if (env_nst > 0 && nst > env_nst) nst = env_nst;
+  if (nst < 2) {
+    set_error("b2l_q4_gemv: K=%d does not leave room for the weight ring", p.K);
+    return B2L_E_UNSUPPORTED;
+  }
+  p.nst = nst;
+  const SmemLayout L = smem_layout(nst, p.K, NDIG);
+  static DynSmemCache smem_cache;
+  if (int rc = ensure_dyn_smem(q4_gemv_kernel<MAXC, NDIG>, L.total, smem_cache)) return rc;
+  int grid = grid_override > 0 ? grid_override : ctas_per_sm * sm_count();
+  if (grid > p.n_rb) grid = p.n_rb;
+  LaunchCfg lc(dim3(grid), dim3(NTHREADS), L.total, stream, pdl, 1);
+  B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, q4_gemv_kernel<MAXC, NDIG>, p));
   return 0;
 }
+}  // namespace
 
 extern "C" int b2l_q4_gemv(const b2l_q4_linear_args* a, b2l_stream_t stream) {
   B2L_CHECK_ARG(a != nullptr, "b2l_q4_gemv: null args");
   B2L_CHECK_ARG(a->x && a->qw_tiled && a->scales && a->zeros && a->y, "b2l_q4_gemv: null pointer");
-  B2L_CHECK_SUPPORTED(a->M == 1, "b2l_q4_gemv: M=%d (this kernel is the batch-1 path; use b2l_q4_linear_tc)", a->M);
-  B2L_CHECK_SUPPORTED(a->K > 0 && a->K % KB == 0 && a->K <= 12 * NCW * 32 * 8, "b2l_q4_gemv: K=%d must be a multiple of %d and <= %d", a->K, KB, 12 * NCW * 32 * 8);
+  B2L_CHECK_SUPPORTED(a->M == 1, "b2l_q4_gemv: M=%d (this kernel is the batch-1 path; use b2l_q4_gemv_batch / b2l_q4_linear_tc)", a->M);
+  B2L_CHECK_SUPPORTED(a->K > 0 && a->K % KB == 0 && a->K <= MAX_K, "b2l_q4_gemv: K=%d must be a multiple of %d and <= %d", a->K, KB, MAX_K);
   B2L_CHECK_ARG(a->N > 0, "b2l_q4_gemv: bad N");
   B2L_CHECK_ARG(((uintptr_t)a->x % 16 == 0) && ((uintptr_t)a->qw_tiled % 16 == 0), "b2l_q4_gemv: x / qw_tiled must be 16-byte aligned");
   B2L_CHECK_ARG(a->sz_dtype == B2L_BF16 || a->sz_dtype == B2L_F32, "b2l_q4_gemv: bad sz_dtype");
@@ -469,27 +522,17 @@ extern "C" int b2l_q4_gemv(const b2l_q4_linear_args* a, b2l_stream_t stream) {
   p.n_rb = (a->N + RB - 1) / RB;
   p.prologue = a->prologue; p.norm_scale = (const __nv_bfloat16*)a->norm_scale; p.eps = a->eps;
   p.epilogue = a->epilogue; p.res = (const __nv_bfloat16*)a->res;
+  p.nst = 0;
   p.tl = (unsigned long long*)a->trace;
   p.nocompute = (a->flags & B2L_F_DEBUG_NOCOMPUTE) ? 1 : 0;
-  // tuning knobs (read once): B2L_GEMV_CTAS_PER_SM (default 2), B2L_GEMV_STAGES (ring depth cap)
+  // tuning knob (read once): B2L_GEMV_CTAS_PER_SM (default 2; K > 16384 runs one CTA per SM with a deeper ring)
   static const int env_cps = [] { const char* e = getenv("B2L_GEMV_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
-  static const int env_nst = [] { const char* e = getenv("B2L_GEMV_STAGES"); return e ? atoi(e) : 0; }();
-  // ring: as deep as fits two CTAs per SM
-  const uint32_t fixed = smem_layout(0, a->K).total;
-  int nst = (int)((110u * 1024u - fixed) / STAGE_BYTES);
-  if (nst > MAX_STAGES) nst = MAX_STAGES;
-  if (env_nst > 0 && nst > env_nst) nst = env_nst;
-  if (nst < 2) nst = 2;
-  p.nst = nst;
-  const SmemLayout L = smem_layout(nst, a->K);
-  const bool wide = a->K > 6 * NCW * 32 * 8;
-  static DynSmemCache smem_cache[2];
-  if (int rc = wide ? ensure_dyn_smem(q4_gemv_kernel<12>, L.total, smem_cache[1]) : ensure_dyn_smem(q4_gemv_kernel<6>, L.total, smem_cache[0]))
-    return rc;
-  int grid = a->split_k > 0 ? a->split_k : (env_cps > 0 ? env_cps : 2) * sm_count();  // split_k doubles as a grid override
-  if (grid > p.n_rb) grid = p.n_rb;
-  LaunchCfg lc(dim3(grid), dim3(NTHREADS), L.total, (cudaStream_t)stream, (a->flags & B2L_F_PDL) != 0, 1);
-  if (wide) B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, q4_gemv_kernel<12>, p));
-  else B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, q4_gemv_kernel<6>, p));
-  return 0;
+  const bool pdl = (a->flags & B2L_F_PDL) != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = a->split_k;  // split_k doubles as a grid override
+  // four digits (|X| < 2^30) while the digit planes leave room for >= 4 ring stages, else three (|X| < 2^22)
+  if (a->K <= 8192) return launch_gemv<6, 4>(p, env_cps > 0 ? env_cps : 2, grid, pdl, st);
+  if (a->K <= 12288) return launch_gemv<6, 3>(p, env_cps > 0 ? env_cps : 2, grid, pdl, st);
+  if (a->K <= 16384) return launch_gemv<12, 3>(p, env_cps > 0 ? env_cps : 2, grid, pdl, st);
+  return launch_gemv<12, 3>(p, 1, grid, pdl, st);
 }

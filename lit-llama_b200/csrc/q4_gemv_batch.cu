@@ -61,7 +61,7 @@ __host__ __device__ inline BSmem bsmem_layout(int nst) {
 
 // ---------------------------------------------------------------- step 1: activations -> fragments
 template <int MAXC>
-__global__ void __launch_bounds__(256) q4_batch_prep_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int K,
+__global__ void __launch_bounds__(256) q4_batch_prep_kernel(const __nv_bfloat16* x, int ldx, int M, int K,
                                                             const __nv_bfloat16* __restrict__ norm_scale, float eps,
                                                             uint32_t* __restrict__ xfrag, float* __restrict__ sums) {
   __shared__ float red[24];
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) q4_batch_prep_kernel(const __nv_bfloat16*
   for (int c = 0; c < MAXC; ++c) {
     const int k = (c * NT + tid) * 8;
     xv[c] = make_uint4(0, 0, 0, 0);
-    if (live && k < K) xv[c] = *reinterpret_cast<const uint4*>(x + (size_t)n * ldx + k);
+    if (live && k < K) xv[c] = ld_coherent_u4(x + (size_t)n * ldx + k);   // written by the previous kernel (PDL): coherent load
   }
   const int nchunk = (K + NT * 8 - 1) / (NT * 8);
   float rinv = 1.f;
@@ -317,12 +317,80 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_batch_kernel(const BParam
   }
 }
 
+// ---------------------------------------------------------------- re-tiling for the mma.sync f16 layout (this kernel's operand)
+__global__ void q4_tile_mma_kernel(const uint8_t* __restrict__ qw, uint32_t* __restrict__ out, int N, int K) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one output word
+  const int n_kb = K / KB;
+  const int n_rb = (N + RB - 1) / RB;
+  const size_t total = (size_t)n_rb * n_kb * 32 * 4;
+  if (idx >= total) return;
+  const int c = idx & 3, lane = (idx >> 2) & 31;
+  const size_t rest = idx >> 7;
+  const int kb = (int)(rest % n_kb), rb = (int)(rest / n_kb);
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t w = 0;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int ss = s & 3;
+    const int row = rb * RB + g + 8 * (ss >> 1);
+    const int k = kb * KB + 16 * c + 2 * t + 8 * (ss & 1) + (s >> 2);
+    if (row < N) {
+      const uint8_t b = qw[(size_t)(k >> 1) * N + row];
+      w |= (uint32_t)((b >> ((k & 1) * 4)) & 0xF) << (4 * s);
+    }
+  }
+  out[idx] = w;
+}
+
+__global__ void q4_untile_mma_kernel(const uint32_t* __restrict__ tiled, uint8_t* __restrict__ qw, int N, int K) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one packed byte [j][o]
+  const size_t total = (size_t)(K / 2) * N;
+  if (idx >= total) return;
+  const int o = (int)(idx % N), j = (int)(idx / N);
+  const int n_kb = K / KB;
+  uint8_t b = 0;
+#pragma unroll
+  for (int nr = 0; nr < 2; ++nr) {
+    const int k = 2 * j + nr;
+    const int kb = k / KB, kl = k % KB, c = kl >> 4, k16 = kl & 15;
+    const int hi8 = k16 >> 3, t = (k16 & 7) >> 1, odd = k16 & 1;
+    const int rb = o / RB, rl = o % RB, g = rl & 7, r8 = rl >> 3;
+    const int s = (r8 << 1 | hi8) + 4 * odd;
+    const uint32_t w = tiled[(((size_t)rb * n_kb + kb) * 32 + (g * 4 + t)) * 4 + c];
+    b |= (uint8_t)(((w >> (4 * s)) & 0xF) << (4 * nr));
+  }
+  qw[idx] = b;
+}
+
 }  // namespace q4mb
 }  // namespace b2l
 
 using namespace b2l;
 using namespace b2l::q4mv;
 using namespace b2l::q4mb;
+
+extern "C" size_t b2l_q4_tiled_mma_bytes(int N, int K) {
+  if (N <= 0 || K <= 0 || K % KB != 0) return 0;
+  return (size_t)((N + RB - 1) / RB) * (K / KB) * KB_BYTES;
+}
+
+extern "C" int b2l_q4_tile_mma(const void* qw, void* qw_tiled, int N, int K, b2l_stream_t stream) {
+  B2L_CHECK_ARG(qw && qw_tiled && N > 0 && K > 0, "b2l_q4_tile_mma: bad argument");
+  B2L_CHECK_SUPPORTED(K % KB == 0, "b2l_q4_tile_mma: in_features %d must be a multiple of %d", K, KB);
+  const size_t total = b2l_q4_tiled_mma_bytes(N, K) / 4;
+  q4_tile_mma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)qw, (uint32_t*)qw_tiled, N, K);
+  B2L_LAUNCH_CHECK("q4_tile_mma_kernel");
+  return 0;
+}
+
+extern "C" int b2l_q4_untile_mma(const void* qw_tiled, void* qw, int N, int K, b2l_stream_t stream) {
+  B2L_CHECK_ARG(qw && qw_tiled && N > 0 && K > 0, "b2l_q4_untile_mma: bad argument");
+  B2L_CHECK_SUPPORTED(K % KB == 0, "b2l_q4_untile_mma: in_features %d must be a multiple of %d", K, KB);
+  const size_t total = (size_t)(K / 2) * N;
+  q4_untile_mma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)qw_tiled, (uint8_t*)qw, N, K);
+  B2L_LAUNCH_CHECK("q4_untile_mma_kernel");
+  return 0;
+}
 
 extern "C" size_t b2l_q4_gemv_batch_workspace_bytes(int K) {
   if (K <= 0 || K % KB) return 0;
@@ -347,8 +415,8 @@ extern "C" int b2l_q4_gemv_batch(const b2l_q4_linear_args* a, b2l_stream_t strea
   else if (a->epilogue == B2L_EPI_SWIGLU) B2L_CHECK_SUPPORTED(a->N % RB == 0, "b2l_q4_gemv_batch: SWIGLU needs N %% 16 == 0");
   else B2L_CHECK_ARG(a->epilogue == B2L_EPI_STORE, "b2l_q4_gemv_batch: bad epilogue %d", a->epilogue);
   cudaStream_t st = (cudaStream_t)stream;
-  // B2L_BATCH_PDL=1: programmatic dependent launch for the two kernels (default: plain stream order)
-  static const int env_pdl = [] { const char* e = getenv("B2L_BATCH_PDL"); return e ? atoi(e) : 0; }();
+  // programmatic dependent launch for the two kernels (B2L_BATCH_PDL=0: plain stream order)
+  static const int env_pdl = [] { const char* e = getenv("B2L_BATCH_PDL"); return e ? atoi(e) : 1; }();
   const bool pdl = (a->flags & B2L_F_PDL) != 0 && env_pdl != 0;
 
   uint8_t* ws = (uint8_t*)a->workspace;

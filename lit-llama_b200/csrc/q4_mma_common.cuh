@@ -1,5 +1,5 @@
-// Pieces shared by the mma.sync int4 decode kernels (q4_gemv.cu: one activation row; q4_gemv_batch.cu: 2..8 rows):
-// tile geometry, mbarrier / TMA / named-barrier wrappers, the shift-free fp16 unpack and the MMA wrapper.
+// Pieces shared by the mma.sync int4 decode kernels (q4_gemv.cu: one activation row, int8 MMA; q4_gemv_batch.cu:
+// 2..8 rows, f16 MMA): tile geometry, mbarrier / TMA / named-barrier wrappers, the MMA wrappers, the f16 unpack.
 #pragma once
 #include "b2l_common.cuh"
 
@@ -73,6 +73,14 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// IMMA.16832.U8.S8: D (16 x 8, s32) += A (16 x 32, u8, row) * B (32 x 8, s8, col)
+__device__ __forceinline__ void mma_u8s8_16832(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 // (w & mask) | magic in one LOP3: masks and magic live in registers

@@ -255,7 +255,7 @@ class _DecodeState:
             self.batch_ws = batch_workspace(device, max(C_, n_hidden))
 
         def q4(lin: ColBlockQuantizedLinear) -> L.Q4Weight:
-            t = lin.tiled_mma() if gemv else lin.tiled()
+            t = (lin.tiled_i8() if B == 1 else lin.tiled_mma()) if gemv else lin.tiled()
             return L.Q4Weight(None if gemv else t.data_ptr(), t.data_ptr() if gemv else None, lin.scales.data_ptr(),
                               lin.zeros.data_ptr(), lin.out_features, lin.in_features)
 
@@ -268,7 +268,7 @@ class _DecodeState:
 
         layers = (L.Layer * cfg.n_layer)()
         for i, blk in enumerate(model.transformer.h):
-            fc12 = model._fc12(i, gemv)
+            fc12 = model._fc12(i, "i8" if B == 1 else ("mma" if gemv else "tc"))
             k, v = model.kv_caches[i]
             layers[i] = L.Layer(
                 rms_1=bf16(blk.rms_1.scale).data_ptr(), rms_2=bf16(blk.rms_2.scale).data_ptr(),
@@ -360,14 +360,15 @@ class LLaMA(nn.Module):
             self._ring.zero_()
 
     # ------------------------------------------------------------------ helpers
-    def _fc12(self, i: int, gemv: bool):
+    def _fc12(self, i: int, kind: str):
         """c_fc1 and c_fc2 of layer i interleaved (8 rows / 8 rows per 16-row block for the
         batch-1 kernel, 64 / 64 per 128-row tile for the tcgen05 kernel) and re-tiled, so one
         tile holds silu's argument and its multiplier and SwiGLU runs in the epilogue."""
         mlp = self.transformer.h[i].mlp
-        key = (gemv, mlp.c_fc1.quant_weight.data_ptr(), mlp.c_fc1.quant_weight._version,
+        gemv = kind != "tc"
+        key = (kind, mlp.c_fc1.quant_weight.data_ptr(), mlp.c_fc1.quant_weight._version,
                mlp.c_fc2.quant_weight.data_ptr(), mlp.c_fc2.quant_weight._version)
-        hit = self._fc12_cache.get((i, gemv))
+        hit = self._fc12_cache.get((i, kind))
         if hit is not None and hit[0] == key:
             return hit[1]
         nh, K = mlp.c_fc1.out_features, mlp.c_fc1.in_features
@@ -381,14 +382,17 @@ class LLaMA(nn.Module):
         scales = inter(mlp.c_fc1.scales, mlp.c_fc2.scales).contiguous()
         zeros = inter(mlp.c_fc1.zeros, mlp.c_fc2.zeros).contiguous()
         lib = L.lib()
-        if gemv:
+        if kind == "i8":
+            tiled = torch.empty(lib.b2l_q4_tiled_i8_bytes(2 * nh, K), dtype=torch.uint8, device=qw.device)
+            L.check(lib.b2l_q4_tile_i8(qw.data_ptr(), tiled.data_ptr(), 2 * nh, K, L.stream_ptr()), "b2l_q4_tile_i8")
+        elif kind == "mma":
             tiled = torch.empty(lib.b2l_q4_tiled_mma_bytes(2 * nh, K), dtype=torch.uint8, device=qw.device)
             L.check(lib.b2l_q4_tile_mma(qw.data_ptr(), tiled.data_ptr(), 2 * nh, K, L.stream_ptr()), "b2l_q4_tile_mma")
         else:
             tiled = torch.empty(lib.b2l_q4_tiled_bytes(2 * nh, K), dtype=torch.uint8, device=qw.device)
             L.check(lib.b2l_q4_tile(qw.data_ptr(), tiled.data_ptr(), 2 * nh, K, L.stream_ptr()), "b2l_q4_tile")
         val = (tiled, scales, zeros)
-        self._fc12_cache[(i, gemv)] = (key, val)
+        self._fc12_cache[(i, kind)] = (key, val)
         return val
 
     def _fast_decode_ok(self) -> bool:

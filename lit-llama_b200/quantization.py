@@ -67,6 +67,8 @@ class ColBlockQuantizedLinear(torch.nn.Module):
         self._tiled_key = None
         self._tiled_mma = None
         self._tiled_mma_key = None
+        self._tiled_i8 = None
+        self._tiled_i8_key = None
 
     # ------------------------------------------------------------------ packing (load-time, any device)
     def pack_weight(self, weight):
@@ -124,8 +126,21 @@ class ColBlockQuantizedLinear(torch.nn.Module):
             self._tiled, self._tiled_key = t, key
         return self._tiled
 
+    def tiled_i8(self) -> torch.Tensor:
+        """The [N/16][K/64][32 lanes][16 B] re-tiling of the batch-1 kernel (b2l_q4_tile_i8: int8-MMA fragments)."""
+        qw = self.quant_weight
+        key = (qw.data_ptr(), qw._version)
+        if self._tiled_i8 is None or self._tiled_i8_key != key:
+            self._check_layout()
+            nbytes = L.lib().b2l_q4_tiled_i8_bytes(self.out_features, self.in_features)
+            t = torch.empty(nbytes, dtype=torch.uint8, device=qw.device)
+            L.check(L.lib().b2l_q4_tile_i8(qw.data_ptr(), t.data_ptr(), self.out_features, self.in_features, L.stream_ptr()),
+                    "b2l_q4_tile_i8")
+            self._tiled_i8, self._tiled_i8_key = t, key
+        return self._tiled_i8
+
     def tiled_mma(self) -> torch.Tensor:
-        """The [N/16][K/64][32 lanes][16 B] re-tiling of the batch-1 kernel (b2l_q4_tile_mma)."""
+        """The [N/16][K/64][32 lanes][16 B] re-tiling of the 2..8-row kernel (b2l_q4_tile_mma: f16-MMA fragments)."""
         qw = self.quant_weight
         key = (qw.data_ptr(), qw._version)
         if self._tiled_mma is None or self._tiled_mma_key != key:
@@ -157,7 +172,7 @@ class ColBlockQuantizedLinear(torch.nn.Module):
         aligned = x.data_ptr() % 16 == 0 and x.stride(0) % 8 == 0
         if self.gemv_capable and aligned and M == 1:
             a = L.Q4LinearArgs(
-                x=x.data_ptr(), ldx=x.stride(0), qw_tiled=self.tiled_mma().data_ptr(), scales=self.scales.data_ptr(),
+                x=x.data_ptr(), ldx=x.stride(0), qw_tiled=self.tiled_i8().data_ptr(), scales=self.scales.data_ptr(),
                 zeros=self.zeros.data_ptr(), sz_dtype=L.sz_dtype_of(self.scales), y=y.data_ptr(), ldy=N, M=1, N=N, K=K,
                 prologue=L.PRO_NONE, norm_scale=None, eps=0.0, epilogue=L.EPI_STORE, res=None, ldres=0, split_k=0, flags=0)
             L.check(L.lib().b2l_q4_gemv(C.byref(a), L.stream_ptr()), "b2l_q4_gemv")

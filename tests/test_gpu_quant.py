@@ -95,29 +95,32 @@ def test_tc_linear_small(dev, N, K, M, S):
                                        (4096, 11008, 77)])
 def test_gemv_small_and_ragged(dev, N, K, grid):
     """Batch-1 kernel: odd block counts (pairs + a single), padded rows, short last stage, forced tiny grids."""
-    from gpu_util import assert_q4_linear_close, gemv_call, rand_q4, tile_mma
+    from gpu_util import assert_q4_linear_close, gemv_call, rand_q4, tile_i8, tile_mma
     from lit_llama_b200 import _lib as L
 
     lv, qw, sc, z = rand_q4(N, K, dev, seed=N + K)
-    qt = tile_mma(L, qw, N, K)
+    qt = tile_i8(L, qw, N, K)
     back = torch.empty_like(qw)
-    L.check(L.lib().b2l_q4_untile_mma(qt.data_ptr(), back.data_ptr(), N, K, L.stream_ptr()), "untile_mma")
+    L.check(L.lib().b2l_q4_untile_i8(qt.data_ptr(), back.data_ptr(), N, K, L.stream_ptr()), "untile_i8")
     assert torch.equal(back, qw)  # the re-tiling is a pure permutation of nibbles
+    back.zero_()
+    L.check(L.lib().b2l_q4_untile_mma(tile_mma(L, qw, N, K).data_ptr(), back.data_ptr(), N, K, L.stream_ptr()), "untile_mma")
+    assert torch.equal(back, qw)  # and so is the f16-fragment tiling of the 2..8-row kernel
     x = torch.randn(1, K, device=dev).bfloat16()
     y, err = gemv_call(L, x, qt, sc, z, N, K, grid=grid)
     torch.cuda.synchronize()
     assert err is None, err
-    assert_q4_linear_close(y, x, lv, sc, z)
+    assert_q4_linear_close(y, x, lv, sc, z, min_equal=0.995)  # exact integer contraction: only double rounding differs
 
 
 def test_gemv_prologue_epilogue_and_determinism(dev):
-    from gpu_util import gemv_call, rand_q4, ref_linear, relerr, tile_mma
+    from gpu_util import gemv_call, rand_q4, ref_linear, relerr, tile_i8
     from lit_llama_b200 import _lib as L
 
     torch.manual_seed(11)
     N, K = 512, 1024
     lv, qw, sc, z = rand_q4(N, K, dev, seed=5)
-    qt = tile_mma(L, qw, N, K)
+    qt = tile_i8(L, qw, N, K)
     x = (torch.randn(1, K, device=dev) * 0.7).bfloat16()
     g = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
     xn = g * (x * torch.rsqrt(torch.mean(x * x, dim=-1, keepdim=True) + 1e-5))  # model.py:270-277 in bf16 on this device
@@ -127,8 +130,8 @@ def test_gemv_prologue_epilogue_and_determinism(dev):
     res = torch.randn(1, N, device=dev).bfloat16()
     y, err = gemv_call(L, x, qt, sc, z, N, K, epilogue=1, res=res)
     want = ref_linear(x, lv, sc, z).float().bfloat16() + res
-    # ~1.5 % of the linear's outputs sit on the other side of a bf16 rounding boundary (Numerics)
-    assert err is None and float((y == want).float().mean()) > 0.93
+    # exact contraction: only the fp32 -> bf16 double rounding can differ from the correctly rounded result
+    assert err is None and float((y == want).float().mean()) > 0.99
     assert relerr(y, want) < 2.0 ** -9
     buf = res.clone()
     _, err = gemv_call(L, x, qt, sc, z, N, K, epilogue=1, res=buf, y=buf)
@@ -137,8 +140,8 @@ def test_gemv_prologue_epilogue_and_determinism(dev):
     a, b = full[:, :, 0].reshape(1, -1), full[:, :, 1].reshape(1, -1)
     y, err = gemv_call(L, x, qt, sc, z, N, K, epilogue=2, n_out=N // 2)
     want = torch.nn.functional.silu(a) * b
-    assert err is None and float((y == want).float().mean()) > 0.88 and relerr(y, want) < 2.0 ** -8
-    # bit-identical across runs and grid sizes (every row's K sum stays inside one CTA, fixed reduction order, no atomics)
+    assert err is None and float((y == want).float().mean()) > 0.97 and relerr(y, want) < 2.0 ** -8
+    # bit-identical across runs and grid sizes (integer accumulation: the result does not depend on any order)
     y0, _ = gemv_call(L, x, qt, sc, z, N, K)
     for grid in (0, 5, 32, 100):
         y1, _ = gemv_call(L, x, qt, sc, z, N, K, grid=grid)
@@ -148,30 +151,30 @@ def test_gemv_prologue_epilogue_and_determinism(dev):
 @pytest.mark.parametrize("N,K,M,grid", [(4096, 4096, 8, 0), (4096, 11008, 5, 0), (22016, 4096, 2, 0), (130, 256, 3, 0), (48, 4096, 8, 2),
                                          (16, 64, 1, 0), (5120, 13824, 8, 0), (4096, 4096, 7, 100)])
 def test_gemv_batch_vs_exact_and_vs_batch1(dev, N, K, M, grid):
-    """The 2..8-row kernel: every row against exact arithmetic, and BIT-identical to the batch-1 kernel on
-    that row (same MMAs, same fixed reduction order; only the activations travel differently)."""
-    from gpu_util import assert_q4_linear_close, gemv_batch_call, gemv_call, rand_q4, tile_mma
+    """The 2..8-row kernel (f16 MMA, fp32 accumulation): every row against exact arithmetic, and within one bf16
+    ulp of the batch-1 kernel (exact integer contraction) on that row, equal almost everywhere."""
+    from gpu_util import assert_q4_linear_close, gemv_batch_call, gemv_call, rand_q4, relerr, tile_i8, tile_mma
     from lit_llama_b200 import _lib as L
 
     lv, qw, sc, z = rand_q4(N, K, dev, seed=N + K + M)
-    qt = tile_mma(L, qw, N, K)
+    qt, q8 = tile_mma(L, qw, N, K), tile_i8(L, qw, N, K)
     x = torch.randn(M, K, device=dev).bfloat16()
     y, err = gemv_batch_call(L, x, qt, sc, z, N, K, grid=grid)
     assert err is None, err
     assert_q4_linear_close(y, x, lv, sc, z)
     for m in range(M):
-        y1, err = gemv_call(L, x[m : m + 1].contiguous(), qt, sc, z, N, K, grid=grid)
+        y1, err = gemv_call(L, x[m : m + 1].contiguous(), q8, sc, z, N, K, grid=grid)
         assert err is None, err
-        assert torch.equal(y[m : m + 1], y1), m
+        assert float((y[m : m + 1] == y1).float().mean()) > 0.85 and relerr(y[m : m + 1], y1) < 2.0 ** -9, m
 
 
 def test_gemv_batch_prologue_epilogue(dev):
-    from gpu_util import gemv_batch_call, gemv_call, rand_q4, tile_mma
+    from gpu_util import gemv_batch_call, gemv_call, rand_q4, relerr, tile_i8, tile_mma
     from lit_llama_b200 import _lib as L
 
     N, K, M = 512, 1024, 6
     lv, qw, sc, z = rand_q4(N, K, dev, seed=5)
-    qt = tile_mma(L, qw, N, K)
+    qt, q8 = tile_mma(L, qw, N, K), tile_i8(L, qw, N, K)
     x = (torch.randn(M, K, device=dev) * 0.7).bfloat16()
     g = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
     res = torch.randn(M, N, device=dev).bfloat16()
@@ -182,9 +185,10 @@ def test_gemv_batch_prologue_epilogue(dev):
             kw1 = dict(kw)
             if "res" in kw1:
                 kw1["res"] = res[m : m + 1].contiguous()
-            y1, err = gemv_call(L, x[m : m + 1].contiguous(), qt, sc, z, N, K, **kw1)
+            y1, err = gemv_call(L, x[m : m + 1].contiguous(), q8, sc, z, N, K, **kw1)
             assert err is None, err
-            assert torch.equal(y[m : m + 1], y1), (kw.keys(), m)
+            # f16-MMA batch kernel vs exact batch-1 kernel: 1-ulp flips only (SwiGLU multiplies two such values)
+            assert float((y[m : m + 1] == y1).float().mean()) > 0.85 and relerr(y[m : m + 1], y1) < 2.0 ** -8, (kw.keys(), m)
     # in place on the residual stream (x + h with y aliasing res), twice the same result
     buf = res.clone()
     y, _ = gemv_batch_call(L, x, qt, sc, z, N, K, epilogue=1, res=res)
@@ -199,11 +203,11 @@ def test_gemv_batch_prologue_epilogue(dev):
                                       ("65B mlp_proj", 8192, 22016)])
 def test_gemv_13b_65b_shapes(dev, name, N, K):
     """The other BASELINE model widths through the batch-1 kernel (K = 22016 exercises the wide-row prologue)."""
-    from gpu_util import gemv_call, rand_q4, ref_linear, relerr, tile_mma
+    from gpu_util import gemv_call, rand_q4, ref_linear, relerr, tile_i8
     from lit_llama_b200 import _lib as L
 
     lv, qw, sc, z = rand_q4(N, K, dev, seed=N % 97 + K)
-    qt = tile_mma(L, qw, N, K)
+    qt = tile_i8(L, qw, N, K)
     x = torch.randn(1, K, device=dev).bfloat16()
     g = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
     y, err = gemv_call(L, x, qt, sc, z, N, K)
@@ -231,14 +235,14 @@ def test_tc_linear_7b_shapes(dev, name, N, K):
     want = ref_linear(x, lv, sc, z)
     assert relerr(y, want) < 1e-3 + 2.0 ** -9
     # the batch-1 kernel on the same weights: same exact-arithmetic target
-    from gpu_util import gemv_call, tile_mma
-    y1, err = gemv_call(L, x[0:1], tile_mma(L, qw, N, K), sc, z, N, K)
+    from gpu_util import gemv_call, tile_i8
+    y1, err = gemv_call(L, x[0:1], tile_i8(L, qw, N, K), sc, z, N, K)
     assert err is None, err
     assert relerr(y1, want[0:1]) < 1e-3 + 2.0 ** -9
-    # two independent kernels: same bf16 results up to 1-ulp flips.  The batch-1 kernel accumulates
-    # (1024 + level) * x in fp32, ~2^-13 relative to the result: a few % of outputs
-    # land on the other side of a bf16 rounding boundary.
-    assert float((y1 == y[0:1]).float().mean()) > 0.85
+    # two independent kernels: same bf16 results up to 1-ulp flips (the tcgen05 kernel accumulates (128 + level) * x
+    # in fp32, the batch-1 kernel is exact: a percent or two of outputs sit on the other side of a rounding boundary)
+    assert float((y1 == want[0:1].float().bfloat16()).float().mean()) > 0.995
+    assert float((y1 == y[0:1]).float().mean()) > 0.9
     assert relerr(y1, y[0:1]) < 2.0 ** -9
     yg = torch.empty(2, N, device=dev, dtype=torch.bfloat16)
     rc = L.lib().b2l_q_linear(x.data_ptr(), K, qw.data_ptr(), sc.data_ptr(), z.data_ptr(), L.sz_dtype_of(sc), None, yg.data_ptr(), N, 2, N, K, 4, K, L.stream_ptr())

@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "grid_flag", "hmma_rate", "imma_rate", "cta_times", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "grid_flag", "hmma_rate", "imma_rate", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline"]
 
 
 _DLIB = None
@@ -110,6 +110,14 @@ def tile_mma(L, qw, N, K):
     return qt
 
 
+def tile_i8(L, qw, N, K):
+    import torch
+
+    qt = torch.empty(L.lib().b2l_q4_tiled_i8_bytes(N, K), dtype=torch.uint8, device=qw.device)
+    L.check(L.lib().b2l_q4_tile_i8(qw.data_ptr(), qt.data_ptr(), N, K, L.stream_ptr()), "tile_i8")
+    return qt
+
+
 def gemv_call(L, x, qt, scales, zeros, N, K, *, y=None, prologue=0, norm_scale=None, eps=1e-5, epilogue=0, res=None, grid=0,
               flags=0, n_out=None):
     import torch
@@ -156,9 +164,9 @@ def sec_gemv():
     for (N, K, grid) in [(16, 64, 0), (16, 128, 0), (32, 2048, 0), (48, 4096, 0), (130, 256, 0), (4096, 4096, 0), (4096, 4096, 7),
                          (12288, 4096, 0), (4096, 11008, 0), (32000, 4096, 0), (22016, 4096, 0), (128, 6400, 0)]:
         lv, qw, sc, z = rand_q4(N, K, dev, seed=N + K)
-        qt = tile_mma(L, qw, N, K)
+        qt = tile_i8(L, qw, N, K)
         back = torch.empty_like(qw)
-        L.check(L.lib().b2l_q4_untile_mma(qt.data_ptr(), back.data_ptr(), N, K, L.stream_ptr()), "untile_mma")
+        L.check(L.lib().b2l_q4_untile_i8(qt.data_ptr(), back.data_ptr(), N, K, L.stream_ptr()), "untile_i8")
         x = torch.randn(1, K, device=dev).bfloat16()
         y, err = gemv_call(L, x, qt, sc, z, N, K, grid=grid)
         torch.cuda.synchronize()
@@ -174,7 +182,7 @@ def sec_gemv():
             print("   want", [round(float(v), 4) for v in want[0, :8]])
     N, K = 512, 1024
     lv, qw, sc, z = rand_q4(N, K, dev, seed=5)
-    qt = tile_mma(L, qw, N, K)
+    qt = tile_i8(L, qw, N, K)
     x = (torch.randn(1, K, device=dev) * 0.7).bfloat16()
     g = (1 + 0.1 * torch.randn(K, device=dev)).bfloat16()
     ms = torch.mean(x * x, dim=-1, keepdim=True)
@@ -211,7 +219,7 @@ def sec_bench_gemv():
     for (name, N, K) in [("c_attn", 12288, 4096), ("c_proj", 4096, 4096), ("fc12", 22016, 4096), ("mlp_proj", 4096, 11008), ("lm_head", 32000, 4096)]:
         lv, qw, sc, z = rand_q4(N, K, dev, seed=3)
         n_copies = max(4, int(400e6 // (N * K // 2)) + 1)
-        qts = [tile_mma(L, qw, N, K) for _ in range(n_copies)]
+        qts = [tile_i8(L, qw, N, K) for _ in range(n_copies)]
         x = torch.randn(1, K, device=dev).bfloat16()
         y = torch.zeros(1, N, device=dev, dtype=torch.bfloat16)
         for grid in (0,):
@@ -597,47 +605,6 @@ def sec_imma_rate():
                       f"{cyc / per_smsp:.2f} clk per MMA per sub-partition", flush=True)
 
 
-def sec_cta_times():
-    """Per-CTA main-loop times of one batch-1 launch per 7B shape: who are the stragglers?"""
-    import torch
-    from lit_llama_b200 import _lib as L
-
-    dev = torch.device("cuda")
-    lib = L.lib()
-    for (name, N, K) in [("c_attn", 12288, 4096), ("fc12", 22016, 4096), ("mlp_proj", 4096, 11008)]:
-        lv, qw, sc, z = rand_q4(N, K, dev, seed=3)
-        qts = [tile_mma(L, qw, N, K) for _ in range(6)]   # rotate copies: weights come from HBM, not L2
-        x = torch.randn(1, K, device=dev).bfloat16()
-        y = torch.zeros(1, N, device=dev, dtype=torch.bfloat16)
-        tl = torch.zeros(64, dtype=torch.int64, device=dev)
-        out = torch.zeros((296, 4), dtype=torch.int64, device=dev)
-        for rep in range(6):
-            tl.zero_(); tl[0] = 2**62; tl[60] = 2**62; tl[61] = 2**62
-            a = L.Q4LinearArgs(x=x.data_ptr(), ldx=K, qw_tiled=qts[rep].data_ptr(), scales=sc.data_ptr(), zeros=z.data_ptr(), sz_dtype=0,
-                               y=y.data_ptr(), ldy=N, M=1, N=N, K=K, prologue=0, norm_scale=None, eps=1e-5, epilogue=0, res=None,
-                               ldres=N, split_k=0, flags=0, trace=tl.data_ptr())
-            L.check(lib.b2l_q4_gemv(C.byref(a), L.stream_ptr()), "gemv")
-            torch.cuda.synchronize()
-        L.check(lib.b2l_debug_gemv_cta_times(out.data_ptr(), 296, L.stream_ptr()), "cta_times")
-        torch.cuda.synchronize()
-        o = out.cpu()
-        t0 = int(o[:, 0].min())
-        loop = (o[:, 1] - o[:, 0]).double() / 1e3
-        per_stage = loop / o[:, 3].double().clamp_min(1)
-        print(f"--- {name}: loop us min {float(loop.min()):.2f} median {float(loop.median()):.2f} max {float(loop.max()):.2f}; "
-              f"stages per CTA {int(o[:, 3].min())}..{int(o[:, 3].max())}; us/stage min {float(per_stage.min()):.3f} median {float(per_stage.median()):.3f} max {float(per_stage.max()):.3f}")
-        # by SM: the two CTAs of an SM, their stage counts and finish times
-        by_sm = {}
-        for c in range(296):
-            by_sm.setdefault(int(o[c, 2]), []).append((c, int(o[c, 3]), (int(o[c, 1]) - t0) / 1e3))
-        rows = sorted(by_sm.items(), key=lambda kv: -max(v[2] for v in kv[1]))
-        print(f"    SMs used {len(by_sm)}; CTAs per SM histogram {sorted(set(len(v) for v in by_sm.values()))}")
-        for sm, v in rows[:6] + rows[-4:]:
-            print(f"    sm {sm:3d}: " + "  ".join(f"cta {c:3d} stages {st:2d} done@{t:.2f}" for c, st, t in v))
-        hist = torch.histc(loop.float(), bins=8, min=float(loop.min()), max=float(loop.max()))
-        print(f"    loop-time histogram ({float(loop.min()):.2f}..{float(loop.max()):.2f} us, 8 bins): {[int(h) for h in hist]}")
-
-
 def sec_trace():
     """clock64 stamps of CTA 0 of one launch: where does a CTA spend its time?"""
     import torch
@@ -955,7 +922,7 @@ def sec_precision():
     dev = torch.device("cuda")
     for N, K in [(4096, 4096), (4096, 11008), (2048, 22016)]:
         lv, qw, sc, z = rand_q4(N, K, dev, seed=3)
-        qm, qt = tile_mma(L, qw, N, K), (tile(L, qw, N, K) if K <= 11008 else None)
+        qm, qt = tile_i8(L, qw, N, K), (tile(L, qw, N, K) if K <= 11008 else None)
         g = torch.Generator(device="cpu").manual_seed(5)
         base = torch.randn(1, K, generator=g)
         spike = base.clone(); spike[0, 16 * 7 + 2] = 60.0; spike[0, 16 * 90 + 11] = -45.0
