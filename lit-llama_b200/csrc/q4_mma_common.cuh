@@ -52,6 +52,7 @@ template <int ID> __device__ __forceinline__ void bar_arrive_c(int n) { asm vola
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
   switch (id) {
     case 1: bar_sync_c<1>(n); break;
+    case 2: bar_sync_c<2>(n); break;
     case 3: bar_sync_c<3>(n); break;
     case 4: bar_sync_c<4>(n); break;
     case 5: bar_sync_c<5>(n); break;
