@@ -290,7 +290,7 @@ typedef struct b2l_decode_args {
   int flags;                 /* B2L_F_*                                               */
   void* timeline;            /* debug: device uint64[(5*n_layer+1)*64] of %globaltimer stamps per
                                 launch (NULL = off); tools/diag.py `timeline`.  With `plan`: uint64
-                                [(5*n_layer+1)*8] per-op stamps of the persistent kernel   */
+                                [(5*n_layer+1)*16] per-op stamps of the persistent kernel   */
   void* batch_work;          /* B in 2..8: scratch of b2l_q4_gemv_batch_workspace_bytes(max K) bytes; the
                                 linears then run on the mma.sync batch kernel (weights need qw_mma).
                                 NULL: tcgen05 kernel (weights need qw_tiled)              */

@@ -35,6 +35,11 @@ int b2l_debug_hmma_rate(void* out, int warps, int chains, int iters, int with_un
  * front of every MMA (2 = the two LOP3 of the int8 form of the int4 unpack).  out: device uint64[2], out[0] = cycles. */
 int b2l_debug_imma_rate(void* out, int warps, int chains, int iters, int n_alu, b2l_stream_t stream);
 
+/* Debug only (tools/diag.py consumer_rate): the decode kernels' consumer loop on stages already resident in shared
+ * memory (no TMA, no barriers): cycles for `iters` sweeps over 8 stages of 16 KB.  mode bits: 1 weight LDS, 2 digit LDS,
+ * 4 IMMA, 8 predicate the digit load of the unused lanes off.  out: device uint64[2], out[0] = cycles (CTA 0). */
+int b2l_debug_consumer_rate(void* out, int warps, int iters, int mode, int n_ctas, b2l_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

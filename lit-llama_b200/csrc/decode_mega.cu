@@ -7,7 +7,7 @@
 //
 // Why one kernel (measured): a 2 x 110 KB-per-SM streaming kernel cannot be co-resident with
 // its successor, so programmatic dependent launch only overlaps kernel TAILS and every one of the 161 launches of a
-// token pays its own ring-fill latency (~2 us of idle HBM per launch at 7B).  Here 2 CTAs per SM stay resident for
+// token pays its own ring-fill latency (~2 us of idle HBM per launch at 7B).  Here one CTA per SM stays resident for
 // the whole token:
 //   * the producer warp of each CTA walks the token's static op list and streams that CTA's share of EVERY op's
 //     weights (and K/V rows) through one mbarrier ring with TMA bulk copies.  Weights never depend on activations,
@@ -55,9 +55,17 @@ struct Params {
   const __nv_bfloat16* qkv; __nv_bfloat16* att; float* attn_work; int* tickets; int n_split;
   float eps; int szdt;
   int nst, kmax;
-  unsigned long long* tl;   // debug timeline [n_ops][8] (nullptr = off)
+  unsigned long long* tl;   // debug timeline [n_ops][16] (nullptr = off)
 };
 
+// One CTA per SM: 16 consumer warps + producer warp + epilogue warp.  (Two 10-warp CTAs per SM, the per-op kernels'
+// shape, were measured first: both CTAs of an SM ran the same activation prologue -- ~150 instructions per 8
+// elements, 1.6 us for K = 11008 -- and kept two copies of the digit planes; profiles/r02_mega_timeline_v1.txt.)
+constexpr int MW = 16;                     // consumer warps
+constexpr int MT = MW * 32;                // consumer threads
+constexpr int M_PRODUCER = MW;             // warp 16
+constexpr int M_THREADS = (MW + 2) * 32;   // 576
+constexpr int M_MAX_STAGES = 12;
 constexpr int HS = 128;                    // head size
 constexpr int KV_ROWS = STAGE_BYTES / (HS * 2);   // 64 K (or V) rows per ring stage
 constexpr int ATT_CHUNK = 128;             // keys per attention work item
@@ -74,9 +82,9 @@ __host__ __device__ inline SmemLayout smem_layout(int nst, int kmax, int ndig) {
   L.ring = o;    o += (uint32_t)nst * STAGE_BYTES;
   L.xf = o;      o += (uint32_t)ndig * plane_stride(kmax);
   L.zero = o;    o += 16;
-  L.scratch = o; o += 2 * NCW * MAX_HALVES * RB * 16;   // 8 KB: GEMV partials; attention: per-warp accumulators (4 KB + 64 B)
-  L.red = o;     o += 192;
-  L.bars = o;    o += 2 * MAX_STAGES * 8;
+  L.scratch = o; o += 2 * MW * MAX_HALVES * RB * 16;    // 16 KB: GEMV partials; attention: per-warp accumulators (8 KB + 128 B)
+  L.red = o;     o += 320;                              // float[16] sumsq, float[16] max, int64[16] sum X, int sh, int last
+  L.bars = o;    o += 2 * M_MAX_STAGES * 8;
   L.total = (o + 127u) & ~127u;
   return L;
 }
@@ -160,19 +168,19 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
 }
 
 template <int MAXC, int NDIG>
-__global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p) {
+__global__ void __launch_bounds__(M_THREADS, 1) decode_mega_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const SmemLayout L = smem_layout(p.nst, p.kmax, NDIG);
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x;
-  const uint32_t bar_full = sbase + L.bars, bar_empty = bar_full + MAX_STAGES * 8;
+  const uint32_t bar_full = sbase + L.bars, bar_empty = bar_full + M_MAX_STAGES * 8;
   const uint32_t PS = plane_stride(p.kmax);
 
   if (tid == 0) {
     for (int i = 0; i < p.nst; ++i) {
       mbar_init(bar_full + i * 8, 1);
-      mbar_init(bar_empty + i * 8, NCW);
+      mbar_init(bar_empty + i * 8, MW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -192,13 +200,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
   const __nv_bfloat16* emb = p.wte + (size_t)tok * p.C;          // transformer.wte(idx), model.py:102
   const int n_items = n_active * p.n_head;                       // attention work items of a layer
 
-  if (warp == PRODUCER_WARP) {
+  if (warp == M_PRODUCER) {
     // ===================== producer: every op's bytes for this CTA, in op order, through one ring =====================
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 1;  // fresh barriers: waiting on parity 1 passes immediately
+      const bool pdbg = (p.tl != nullptr && blockIdx.x == 0);
       for (int oi = 0; oi < p.n_ops; ++oi) {
         const Op& op = p.ops[oi];
+        long long pw = 0;
         if (op.kind == OP_GEMV) {
           int rb_lo, rb_hi;
           op_range(op, rb_lo, rb_hi);
@@ -210,7 +220,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
             for (int kb0 = 0; kb0 < n_kb; kb0 += per_stage) {
               const int nkb = min(per_stage, n_kb - kb0);
               const uint32_t bytes = (uint32_t)nkb * KB_BYTES;
+              const long long c0 = pdbg ? clock64() : 0;
               mbar_wait_b(bar_empty + slot * 8, phase, p.error);
+              if (pdbg) pw += clock64() - c0;
               mbar_expect_tx(bar_full + slot * 8, bytes * halves);
               for (int h = 0; h < halves; ++h)
                 tma_bulk_g2s(sbase + L.ring + slot * STAGE_BYTES + h * HALF_STAGE_BYTES,
@@ -242,15 +254,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
             }
           }
         }
+        if (pdbg) { p.tl[oi * 16 + 7] = (unsigned long long)pw; }
       }
     }
-  } else if (warp < NCW) {
+  } else if (warp < MW) {
     // ===================== consumer warps =====================
-    constexpr int NT = NCW * 32;   // 256
+    constexpr int NT = MT;   // 512
     float* red = reinterpret_cast<float*>(smem + L.red);
-    long long* red_sx = reinterpret_cast<long long*>(smem + L.red + 64);
-    int* red_sh = reinterpret_cast<int*>(smem + L.red + 128);
-    int* red_last = reinterpret_cast<int*>(smem + L.red + 132);
+    long long* red_sx = reinterpret_cast<long long*>(smem + L.red + 128);
+    int* red_sh = reinterpret_cast<int*>(smem + L.red + 256);
+    int* red_last = reinterpret_cast<int*>(smem + L.red + 260);
     int* scratch = reinterpret_cast<int*>(smem + L.scratch);
     const int ncol = lane >> 2, t4 = lane & 3;
     const uint8_t* xf_lane = (ncol < NDIG) ? smem + L.xf + ncol * PS + t4 * 16 : smem + L.zero;
@@ -277,7 +290,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
           if (tid == 0) flag_wait(p.counters + oi - 1, (unsigned int)G, p.error);
           named_bar_sync(2, NT);
         }
-        if (dbg) { atomicMin(p.tl + oi * 8 + 5, globaltimer_ns()); if (blockIdx.x == 0) p.tl[oi * 8 + 0] = globaltimer_ns(); }
+        if (dbg) { atomicMin(p.tl + oi * 16 + 5, globaltimer_ns()); if (blockIdx.x == 0) p.tl[oi * 16 + 0] = globaltimer_ns(); }
         const __nv_bfloat16* xin = op.x_is_emb ? emb : op.x;
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
@@ -310,11 +323,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
         }
         ss = warp_sum(ss);
         mx = warp_max(mx);
-        if (lane == 0) { red[warp] = ss; red[8 + warp] = mx; }
+        if (lane == 0) { red[warp] = ss; red[MW + warp] = mx; }
         named_bar_sync(1, NT);
         ss = 0.f; mx = 0.f;
 #pragma unroll
-        for (int w = 0; w < NCW; ++w) { ss += red[w]; mx = fmaxf(mx, red[8 + w]); }
+        for (int w = 0; w < MW; ++w) { ss += red[w]; mx = fmaxf(mx, red[MW + w]); }
         float rinv = 1.f;
         if (norm) {
           rinv = rms_rinv(ss, K, p.eps);
@@ -370,13 +383,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
         if (lane == 0) red_sx[warp] = sx;
         if (tid == 0) *red_sh = sh;
         named_bar_sync(3, NT + 32);   // digit planes, sum X and sh are ready (releases the epilogue warp too)
-        if (dbg && blockIdx.x == 0) p.tl[oi * 8 + 1] = globaltimer_ns();
+        if (dbg && blockIdx.x == 0) p.tl[oi * 16 + 1] = globaltimer_ns();
 
-        // ---- weights: stage -> registers -> IMMA.  A stage holds 32 tiles of 512 B; warp w takes tiles w + 8 i.
+        // ---- weights: stage -> registers -> IMMA.  A stage holds 32 tiles of 512 B; warp w takes tiles w and w + 16.
         int rb_lo, rb_hi;
         op_range(op, rb_lo, rb_hi);
         const int n_kb = K / KB;
         int u = 0;
+        long long cw = 0, bw = 0;
+        const long long l0 = clock64();
         for (int rb = rb_lo; rb < rb_hi; rb += 2, ++u) {
           const int halves = min(2, rb_hi - rb);
           int acc[MAX_HALVES][2][4];
@@ -387,66 +402,65 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
 #pragma unroll
               for (int i = 0; i < 4; ++i) acc[h][c][i] = 0;
           const int per_stage = halves == 2 ? KBP_PER_STAGE : 2 * KBP_PER_STAGE;
-          for (int kb0 = 0; kb0 < n_kb; kb0 += per_stage) {
-            const int nkb = min(per_stage, n_kb - kb0);
-            mbar_wait_b(bar_full + slot * 8, phase, p.error);
-            const uint8_t* st = smem + L.ring + slot * STAGE_BYTES + lane * 16;
-            const uint8_t* xq = xf_lane + kb0 * xf_step;
-            if (halves == 2) {
-              // tiles w, w + 8 of half 0 at 0 .. 8 KB, of half 1 at 8 KB ..: the B fragments are shared by the halves
-              if (nkb == KBP_PER_STAGE) {
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                  const int kbl = i * NCW + warp;
-                  const uint4 xb = *reinterpret_cast<const uint4*>(xq + kbl * xf_step);
-                  tile_imma(acc[0][0], acc[0][1], st + kbl * KB_BYTES, xb);
-                  tile_imma(acc[1][0], acc[1][1], st + HALF_STAGE_BYTES + kbl * KB_BYTES, xb);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                  const int kbl = i * NCW + warp;
-                  if (kbl < nkb) {
-                    const uint4 xb = *reinterpret_cast<const uint4*>(xq + kbl * xf_step);
-                    tile_imma(acc[0][0], acc[0][1], st + kbl * KB_BYTES, xb);
-                    tile_imma(acc[1][0], acc[1][1], st + HALF_STAGE_BYTES + kbl * KB_BYTES, xb);
-                  }
-                }
-              }
-            } else {
-              // one 16-row block: the stage holds 32 k-block positions of it
-              if (nkb == 2 * KBP_PER_STAGE) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int kbl = i * NCW + warp;
-                  const uint4 xb = *reinterpret_cast<const uint4*>(xq + kbl * xf_step);
-                  tile_imma(acc[i & 1][0], acc[i & 1][1], st + kbl * KB_BYTES, xb);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int kbl = i * NCW + warp;
-                  if (kbl < nkb) {
-                    const uint4 xb = *reinterpret_cast<const uint4*>(xq + kbl * xf_step);
-                    tile_imma(acc[i & 1][0], acc[i & 1][1], st + kbl * KB_BYTES, xb);
-                  }
-                }
-              }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + slot * 8);
+          const int n_st = (n_kb + per_stage - 1) / per_stage;
+          const int posB = halves == 2 ? warp : warp + MW;   // k-block position (inside a stage) of this warp's second tile
+          // Two stages per round: both full-barrier waits, then 8 shared-memory loads, then 8 IMMAs, then both releases.
+          // (One stage per round left each warp 4 IMMAs behind a ~250-cycle wait/load/arrive chain: measured 590
+          // cycles per 16 KB stage per SM, barely above the HBM rate; profiles/r02_mega_timeline_v2.txt.)
+          // A warp's tiles sit at the same addresses for one- and two-half units: tile w and tile 16 + w of the stage.
+          for (int s0 = 0; s0 < n_st; s0 += 2) {
+            const bool two = s0 + 1 < n_st;
+            const int slot_a = slot;
+            const uint32_t phase_a = phase;
             if (++slot == p.nst) { slot = 0; phase ^= 1; }
+            const int slot_b = slot;
+            const uint32_t phase_b = phase;
+            if (two) { if (++slot == p.nst) { slot = 0; phase ^= 1; } }
+            const long long c0 = (dbg && blockIdx.x == 0) ? clock64() : 0;
+            mbar_wait_b(bar_full + slot_a * 8, phase_a, p.error);
+            if (two) mbar_wait_b(bar_full + slot_b * 8, phase_b, p.error);
+            if (dbg && blockIdx.x == 0) cw += clock64() - c0;
+            const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+            const int kb_a = s0 * per_stage, kb_b = kb_a + per_stage;
+            const int nkb_a = min(per_stage, n_kb - kb_a), nkb_b = two ? min(per_stage, n_kb - kb_b) : 0;
+            const uint8_t* sta = smem + L.ring + slot_a * STAGE_BYTES + warp * KB_BYTES + lane * 16;
+            const uint8_t* stb = smem + L.ring + slot_b * STAGE_BYTES + warp * KB_BYTES + lane * 16;
+            const uint4 wa0 = *reinterpret_cast<const uint4*>(sta), wa1 = *reinterpret_cast<const uint4*>(sta + HALF_STAGE_BYTES);
+            const uint4 xa0 = warp < nkb_a ? *reinterpret_cast<const uint4*>(xf_lane + (kb_a + warp) * xf_step) : zero4;
+            const uint4 xa1 = posB < nkb_a ? *reinterpret_cast<const uint4*>(xf_lane + (kb_a + posB) * xf_step) : zero4;
+            uint4 wb0 = zero4, wb1 = zero4, xb0 = zero4, xb1 = zero4;
+            if (two) {
+              wb0 = *reinterpret_cast<const uint4*>(stb); wb1 = *reinterpret_cast<const uint4*>(stb + HALF_STAGE_BYTES);
+              if (warp < nkb_b) xb0 = *reinterpret_cast<const uint4*>(xf_lane + (kb_b + warp) * xf_step);
+              if (posB < nkb_b) xb1 = *reinterpret_cast<const uint4*>(xf_lane + (kb_b + posB) * xf_step);
+            }
+            // a tile whose k-block position lies beyond the stage multiplies stale bytes by zero digits
+            mma_u8s8_16832(acc[0][0], wa0.x, wa0.x & 0xf0f0f0f0u, wa0.y, wa0.y & 0xf0f0f0f0u, xa0.x, xa0.y);
+            mma_u8s8_16832(acc[0][1], wa0.z, wa0.z & 0xf0f0f0f0u, wa0.w, wa0.w & 0xf0f0f0f0u, xa0.z, xa0.w);
+            mma_u8s8_16832(acc[1][0], wa1.x, wa1.x & 0xf0f0f0f0u, wa1.y, wa1.y & 0xf0f0f0f0u, xa1.x, xa1.y);
+            mma_u8s8_16832(acc[1][1], wa1.z, wa1.z & 0xf0f0f0f0u, wa1.w, wa1.w & 0xf0f0f0f0u, xa1.z, xa1.w);
+            mma_u8s8_16832(acc[0][0], wb0.x, wb0.x & 0xf0f0f0f0u, wb0.y, wb0.y & 0xf0f0f0f0u, xb0.x, xb0.y);
+            mma_u8s8_16832(acc[0][1], wb0.z, wb0.z & 0xf0f0f0f0u, wb0.w, wb0.w & 0xf0f0f0f0u, xb0.z, xb0.w);
+            mma_u8s8_16832(acc[1][0], wb1.x, wb1.x & 0xf0f0f0f0u, wb1.y, wb1.y & 0xf0f0f0f0u, xb1.x, xb1.y);
+            mma_u8s8_16832(acc[1][1], wb1.z, wb1.z & 0xf0f0f0f0u, wb1.w, wb1.w & 0xf0f0f0f0u, xb1.z, xb1.w);
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(bar_empty + slot_a * 8);
+              if (two) mbar_arrive(bar_empty + slot_b * 8);
+            }
           }
           // lane (g, t): rows g (c0, c1) and g + 8 (c2, c3), digits 2t, 2t + 1.  row g = D[g] - D[g+8], row g+8 = D[g+8] / 16
           const int buf = u & 1;
+          const long long b0 = (dbg && blockIdx.x == 0) ? clock64() : 0;
           named_bar_sync(4 + buf, NT + 32);   // the epilogue warp has drained this scratch buffer
+          if (dbg && blockIdx.x == 0) bw += clock64() - b0;
           if (t4 < 2) {
             if (halves == 2) {
 #pragma unroll
               for (int h = 0; h < MAX_HALVES; ++h) {
                 const int c0 = acc[h][0][0] + acc[h][1][0], c1 = acc[h][0][1] + acc[h][1][1];
                 const int c2 = acc[h][0][2] + acc[h][1][2], c3 = acc[h][0][3] + acc[h][1][3];
-                int* dst = scratch + (((buf * NCW + warp) * MAX_HALVES + h) * RB + (lane >> 2)) * 4 + 2 * t4;
+                int* dst = scratch + (((buf * MW + warp) * MAX_HALVES + h) * RB + (lane >> 2)) * 4 + 2 * t4;
                 *reinterpret_cast<int2*>(dst) = make_int2(c0 - c2, c1 - c3);
                 *reinterpret_cast<int2*>(dst + 8 * 4) = make_int2(c2 >> 4, c3 >> 4);
               }
@@ -455,7 +469,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
               const int c1 = acc[0][0][1] + acc[0][1][1] + acc[1][0][1] + acc[1][1][1];
               const int c2 = acc[0][0][2] + acc[0][1][2] + acc[1][0][2] + acc[1][1][2];
               const int c3 = acc[0][0][3] + acc[0][1][3] + acc[1][0][3] + acc[1][1][3];
-              int* dst = scratch + (((buf * NCW + warp) * MAX_HALVES + 0) * RB + (lane >> 2)) * 4 + 2 * t4;
+              int* dst = scratch + (((buf * MW + warp) * MAX_HALVES + 0) * RB + (lane >> 2)) * 4 + 2 * t4;
               *reinterpret_cast<int2*>(dst) = make_int2(c0 - c2, c1 - c3);
               *reinterpret_cast<int2*>(dst + 8 * 4) = make_int2(c2 >> 4, c3 >> 4);
             }
@@ -463,17 +477,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
           __syncwarp();
           named_bar_arrive(6 + buf, NT + 32);
         }
-        if (dbg) { atomicMax(p.tl + oi * 8 + 3, globaltimer_ns()); if (blockIdx.x == 0) p.tl[oi * 8 + 2] = globaltimer_ns(); }
+        if (dbg) { atomicMax(p.tl + oi * 16 + 3, globaltimer_ns()); if (blockIdx.x == 0) { p.tl[oi * 16 + 2] = globaltimer_ns(); p.tl[oi * 16 + 6] = (unsigned long long)cw; p.tl[oi * 16 + 8] = (unsigned long long)bw; p.tl[oi * 16 + 9] = (unsigned long long)(clock64() - l0); p.tl[oi * 16 + 12] = (unsigned long long)u; } }
       } else {
         // ===================== attention work items =====================
         if (oi > 0) {
           if (tid == 0) flag_wait(p.counters + oi - 1, (unsigned int)G, p.error);
           named_bar_sync(2, NT);
         }
-        if (dbg) { atomicMin(p.tl + oi * 8 + 5, globaltimer_ns()); if (blockIdx.x == 0) p.tl[oi * 8 + 0] = globaltimer_ns(); }
-        float* sm_acc = reinterpret_cast<float*>(smem + L.scratch);     // [NCW][HS]
-        float* sm_m = sm_acc + NCW * HS;                                // [NCW]
-        float* sm_l = sm_m + NCW;                                       // [NCW]
+        if (dbg) { atomicMin(p.tl + oi * 16 + 5, globaltimer_ns()); if (blockIdx.x == 0) p.tl[oi * 16 + 0] = globaltimer_ns(); }
+        float* sm_acc = reinterpret_cast<float*>(smem + L.scratch);     // [MW][HS]
+        float* sm_m = sm_acc + MW * HS;                                 // [MW]
+        float* sm_l = sm_m + MW;                                        // [MW]
         const int grp = lane >> 3, sub8 = lane & 7, d0 = sub8 * 16;
         const int C = p.C;
         for (int w = cta_eff(op); w < n_items; w += G) {
@@ -512,7 +526,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
           float m = -INFINITY, l = 0.f, acc[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-          // old rows: (K stage, V stage) pairs of up to 64 rows; warp w handles rows 8 w .. 8 w + 7 (4 keys x 2 rounds)
+          // old rows: (K stage, V stage) pairs of up to 64 rows; warp w handles rows 4 w .. 4 w + 3 (8 lanes per key)
           for (int sub = 0; sub * KV_ROWS < n_old; ++sub) {
             const int cnt = min(KV_ROWS, n_old - sub * KV_ROWS);
             const int slot_k = slot;
@@ -524,10 +538,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
             mbar_wait_b(bar_full + slot_k * 8, phase_k, p.error);
             const uint8_t* kst = smem + L.ring + slot_k * STAGE_BYTES;
             const uint8_t* vst = smem + L.ring + slot_v * STAGE_BYTES;
-            float sc[2];
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-              const int r = warp * 8 + it * 4 + grp;
+            const int r = warp * 4 + grp;
+            float sc;
+            {
               const int rc = r < cnt ? r : 0;
               const uint4* kr = reinterpret_cast<const uint4*>(kst + (size_t)rc * HS * 2 + d0 * 2);
               float kf[16];
@@ -538,25 +551,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
               s_ += __shfl_xor_sync(0xffffffffu, s_, 1);
               s_ += __shfl_xor_sync(0xffffffffu, s_, 2);
               s_ += __shfl_xor_sync(0xffffffffu, s_, 4);
-              sc[it] = s_;
+              sc = s_;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + slot_k * 8);
             mbar_wait_b(bar_full + slot_v * 8, phase_v, p.error);
+            if (r < cnt) {
+              const uint4* vr = reinterpret_cast<const uint4*>(vst + (size_t)r * HS * 2 + d0 * 2);
+              float vf[16];
+              bf16x8_to_f32(vr[0], vf); bf16x8_to_f32(vr[1], vf + 8);
+              const float mn = fmaxf(m, sc);
+              const float corr = __expf(m - mn), pj = __expf(sc - mn);
+              l = l * corr + pj;
 #pragma unroll
-            for (int it = 0; it < 2; ++it) {
-              const int r = warp * 8 + it * 4 + grp;
-              if (r < cnt) {
-                const uint4* vr = reinterpret_cast<const uint4*>(vst + (size_t)r * HS * 2 + d0 * 2);
-                float vf[16];
-                bf16x8_to_f32(vr[0], vf); bf16x8_to_f32(vr[1], vf + 8);
-                const float mn = fmaxf(m, sc[it]);
-                const float corr = __expf(m - mn), pj = __expf(sc[it] - mn);
-                l = l * corr + pj;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = fmaf(pj, vf[i], acc[i] * corr);
-                m = mn;
-              }
+              for (int i = 0; i < 16; ++i) acc[i] = fmaf(pj, vf[i], acc[i] * corr);
+              m = mn;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + slot_v * 8);
@@ -619,12 +628,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
           named_bar_sync(1, NT);
           float M = -INFINITY;
 #pragma unroll
-          for (int ww = 0; ww < NCW; ++ww) M = fmaxf(M, sm_m[ww]);
+          for (int ww = 0; ww < MW; ++ww) M = fmaxf(M, sm_m[ww]);
           float Ls = 0.f, a = 0.f;
           const int d = tid & (HS - 1);
           const bool writer = tid < HS;
 #pragma unroll
-          for (int ww = 0; ww < NCW; ++ww) {
+          for (int ww = 0; ww < MW; ++ww) {
             const float wg = (sm_m[ww] == -INFINITY) ? 0.f : __expf(sm_m[ww] - M);
             Ls += sm_l[ww] * wg;
             a += sm_acc[ww * HS + d] * wg;
@@ -678,52 +687,66 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
         // every CTA arrives once per op: its items (and any merge it performed) are stored
         named_bar_sync(2, NT);
         if (tid == 0) {
-          __threadfence();
-          red_release(p.counters + oi);
-          if (dbg) { atomicMax(p.tl + oi * 8 + 4, globaltimer_ns()); }
+          red_release(p.counters + oi);   // release: the barrier above orders every thread's stores before it
+          if (dbg) { atomicMax(p.tl + oi * 16 + 4, globaltimer_ns()); }
         }
       }
     }
   } else {
     // ===================== epilogue warp: lane = row of the 32-row unit =====================
-    const long long* red_sx = reinterpret_cast<const long long*>(smem + L.red + 64);
-    const int* red_sh = reinterpret_cast<const int*>(smem + L.red + 128);
+    const long long* red_sx = reinterpret_cast<const long long*>(smem + L.red + 128);
+    const int* red_sh = reinterpret_cast<const int*>(smem + L.red + 256);
     const int* scratch = reinterpret_cast<const int*>(smem + L.scratch);
-    constexpr int NB = NCW * 32 + 32;
+    constexpr int NB = MT + 32;
+    const int half = lane >> 4, row = lane & 15;
     for (int oi = 0; oi < p.n_ops; ++oi) {
       const Op& op = p.ops[oi];
       if (op.kind != OP_GEMV) continue;
       int rb_lo, rb_hi;
       op_range(op, rb_lo, rb_hi);
       const int n_units = (rb_hi - rb_lo + 1) / 2;
+      const __nv_bfloat16* resp = op.res_is_emb ? emb : op.res;
+      // scale / zero / residual of a unit: weights, and a residual stream that was complete two ops ago -- fetched
+      // BEFORE this op's dependency resolves (first unit) or while the consumers stream the unit (later ones)
+      auto fetch = [&](int u, float& sc, float& zero, float& resv) {
+        const int rb = rb_lo + 2 * u;
+        const int orow = (rb + half) * RB + row;
+        const int o = min(orow, op.N - 1);
+        sc = load_sz(op.scales, p.szdt, o);
+        zero = load_sz(op.zeros, p.szdt, o);
+        resv = 0.f;
+        if (op.epilogue == B2L_EPI_RESIDUAL && half < min(2, rb_hi - rb) && orow < op.N)
+          resv = op.res_is_emb ? bf2f(resp[orow]) : ld_cg_bf16(resp + orow);
+      };
+      float sc = 0.f, zero = 0.f, resv = 0.f;
+      if (n_units > 0) fetch(0, sc, zero, resv);
       named_bar_sync(3, NB);
+      long long ew = 0;
+      const long long et0 = clock64();
       long long sum_x = 0;
 #pragma unroll
-      for (int w = 0; w < NCW; ++w) sum_x += red_sx[w];
+      for (int w = 0; w < MW; ++w) sum_x += red_sx[w];
       const double dsum_x = (double)sum_x;
       const int sh = *red_sh;
       const double inv_scale = __longlong_as_double((long long)(1023 - sh) << 52);
       if (n_units > 0) named_bar_arrive(4, NB);
       if (n_units > 1) named_bar_arrive(5, NB);
-      const __nv_bfloat16* resp = op.res_is_emb ? emb : op.res;
       for (int u = 0; u < n_units; ++u) {
         const int rb = rb_lo + 2 * u;
         const int halves = min(2, rb_hi - rb);
         const int buf = u & 1;
-        const int half = lane >> 4, row = lane & 15;
         const bool active = half < halves;
         const int orow = (rb + half) * RB + row;
-        const int o = min(orow, op.N - 1);
-        const float sc = load_sz(op.scales, p.szdt, o);
-        const float zero = load_sz(op.zeros, p.szdt, o);
-        float resv = 0.f;
-        if (op.epilogue == B2L_EPI_RESIDUAL && active && orow < op.N) resv = op.res_is_emb ? bf2f(resp[orow]) : ld_cg_bf16(resp + orow);
+        float sc_n = 0.f, zero_n = 0.f, resv_n = 0.f;
+        if (u + 1 < n_units) fetch(u + 1, sc_n, zero_n, resv_n);
+        const long long e0 = (p.tl != nullptr) ? clock64() : 0;
         named_bar_sync(6 + buf, NB);
+        if (p.tl != nullptr) ew += clock64() - e0;
         int d0 = 0, d1 = 0, d2 = 0, d3 = 0;
         const int hsel = active ? half : 0;
 #pragma unroll
-        for (int w = 0; w < NCW; ++w) {
-          const int4 v = *reinterpret_cast<const int4*>(scratch + (((buf * NCW + w) * MAX_HALVES + hsel) * RB + row) * 4);
+        for (int w = 0; w < MW; ++w) {   // integer sums: exact, independent of the order
+          const int4 v = *reinterpret_cast<const int4*>(scratch + (((buf * MW + w) * MAX_HALVES + hsel) * RB + row) * 4);
           d0 += v.x; d1 += v.y; d2 += v.z; d3 += v.w;
         }
         if (u + 2 < n_units) named_bar_arrive(4 + buf, NB);
@@ -739,11 +762,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
         } else if (active && orow < op.N) {
           op.y[orow] = f2bf(op.epilogue == B2L_EPI_RESIDUAL ? v + resv : v);
         }
+        sc = sc_n; zero = zero_n; resv = resv_n;
       }
-      // this CTA's rows of the op are stored: arrive (the last op's last arriver re-arms the step)
+      // this CTA's rows of the op are stored: arrive (release; __syncwarp orders the other lanes' stores before it).
+      // The last op's last arriver re-arms the step.
       __syncwarp();
       if (lane == 0) {
-        __threadfence();
         if (oi + 1 < p.n_ops) {
           red_release(p.counters + oi);
         } else {
@@ -756,7 +780,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) decode_mega_kernel(const Params p
             __threadfence();
           }
         }
-        if (p.tl != nullptr) atomicMax(p.tl + oi * 8 + 4, globaltimer_ns());
+        if (p.tl != nullptr) atomicMax(p.tl + oi * 16 + 4, globaltimer_ns());
+        if (p.tl != nullptr && blockIdx.x == 0) { p.tl[oi * 16 + 10] = (unsigned long long)ew; p.tl[oi * 16 + 11] = (unsigned long long)(clock64() - et0); }
       }
     }
   }
@@ -825,7 +850,7 @@ extern "C" int b2l_decode_plan_build(const b2l_decode_args* d, b2l_stream_t stre
     o.norm_scale = (const __nv_bfloat16*)norm_scale;
     return o;
   };
-  const int G = 2 * sm_count();
+  const int G = sm_count();
   int oi = 0;
   for (int l = 0; l < d->n_layer; ++l) {
     const b2l_layer& L = d->layers[l];
@@ -873,10 +898,10 @@ namespace b2l {
 
 template <int MAXC, int NDIG>
 static int launch_mega(const b2l_decode_args* d, mega::Params p, cudaStream_t st) {
-  const uint32_t budget = 110u * 1024u;
+  const uint32_t budget = 226u * 1024u;
   const uint32_t fixed = mega::smem_layout(0, p.kmax, NDIG).total;
   int nst = fixed + 2 * STAGE_BYTES <= budget ? (int)((budget - fixed) / STAGE_BYTES) : 0;
-  if (nst > MAX_STAGES) nst = MAX_STAGES;
+  if (nst > mega::M_MAX_STAGES) nst = mega::M_MAX_STAGES;
   static const int env_nst = [] { const char* e = getenv("B2L_MEGA_STAGES"); return e ? atoi(e) : 0; }();
   if (env_nst > 0 && nst > env_nst) nst = env_nst;
   if (nst < 2) {
@@ -888,17 +913,17 @@ static int launch_mega(const b2l_decode_args* d, mega::Params p, cudaStream_t st
   static DynSmemCache smem_cache;
   if (int rc = ensure_dyn_smem(mega::decode_mega_kernel<MAXC, NDIG>, L.total, smem_cache)) return rc;
   int occ = 0;
-  B2L_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega::decode_mega_kernel<MAXC, NDIG>, NTHREADS, L.total));
-  if (occ < 2) {
-    set_error("b2l_decode_step: the persistent kernel needs 2 CTAs per SM (occupancy %d)", occ);
+  B2L_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega::decode_mega_kernel<MAXC, NDIG>, mega::M_THREADS, L.total));
+  if (occ < 1) {
+    set_error("b2l_decode_step: the persistent kernel does not fit an SM (occupancy %d)", occ);
     return B2L_E_UNSUPPORTED;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * sm_count());
-  cfg.blockDim = dim3(NTHREADS);
+  cfg.gridDim = dim3(sm_count());
+  cfg.blockDim = dim3(mega::M_THREADS);
   cfg.dynamicSmemBytes = L.total;
   cfg.stream = st;
-  // all CTAs must be co-resident (the op counters are grid-wide dependencies): 2 per SM by construction, and
+  // all CTAs must be co-resident (the op counters are grid-wide dependencies): one per SM by construction, and
   // declared to the driver as a cooperative launch (B2L_MEGA_COOP=0: plain launch)
   static const int env_coop = [] { const char* e = getenv("B2L_MEGA_COOP"); return e ? atoi(e) : 1; }();
   cudaLaunchAttribute attr[1];
@@ -934,8 +959,9 @@ int decode_step_persistent(const b2l_decode_args* d, b2l_stream_t stream) {
   p.kmax = mega_kmax(d);
   p.tl = (unsigned long long*)d->timeline;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p.kmax <= 8192) return launch_mega<6, 4>(d, p, st);
-  return launch_mega<6, 3>(d, p, st);
+  // four digits (|X| < 2^30) up to K = 8192, three (|X| < 2^22, smaller planes, deeper ring) above
+  if (p.kmax <= 8192) return launch_mega<2, 4>(d, p, st);
+  return launch_mega<3, 3>(d, p, st);
 }
 
 }  // namespace b2l

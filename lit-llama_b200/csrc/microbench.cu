@@ -288,6 +288,77 @@ extern "C" int b2l_debug_imma_rate(void* out, int warps, int chains, int iters, 
   return 0;
 }
 
+// ---- the decode kernels' consumer loop in isolation: `warps` warps sweep 16 KB stages that already sit in shared
+// memory (no TMA, no barriers): per stage a warp loads its two 512-byte tiles (LDS.128 each), its activation-digit
+// fragments (LDS.128, lanes 16..31 read a zero block or are predicated off) and issues 4 IMMA.16832.U8.S8.
+// mode bits: 1 = weight loads, 2 = digit loads, 4 = IMMAs, 8 = predicate the digit load of lanes 16..31 off,
+// 16 = 8 warps x 4 tiles instead of 16 x 2.  out[0] = cycles for `iters` sweeps over 8 stages.
+__global__ void __launch_bounds__(512) consumer_rate_kernel(unsigned long long* out, int iters, int mode) {
+  extern __shared__ __align__(128) uint8_t csm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  constexpr int NST = 8, STAGE = 16384, PS = 4096 + 64;
+  uint8_t* ring = csm;
+  uint8_t* xf = csm + NST * STAGE;
+  uint8_t* zero = xf + 4 * PS;
+  for (int i = tid; i < (NST * STAGE + 4 * PS + 16) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(csm)[i] = 0x01030507u * (i + 1);
+  if (tid < 4) reinterpret_cast<uint32_t*>(zero)[tid] = 0u;
+  __syncthreads();
+  const int ncol = lane >> 2, t4 = lane & 3;
+  const bool pred_off = (mode & 8) != 0;
+  const uint8_t* xf_lane = (ncol < 4) ? xf + ncol * PS + t4 * 16 : zero;
+  const int xf_step = (ncol < 4) ? 64 : 0;
+  const int tiles = 32 / nw;   // tiles per warp per stage
+  int acc[4][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[c][i] = 0;
+  uint4 wv = make_uint4(lane, lane * 3, lane * 5, lane * 7), xb = make_uint4(1, 2, 3, 4);
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+    for (int st = 0; st < NST; ++st) {
+      const uint8_t* base = ring + st * STAGE + lane * 16;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < tiles) {
+          const int tile = i * nw + warp;
+          if (mode & 1) wv = *reinterpret_cast<const uint4*>(base + tile * 512);
+          if (mode & 2) {
+            if (!pred_off || ncol < 4) xb = *reinterpret_cast<const uint4*>(xf_lane + ((st * 16 + tile) & 63) * xf_step);
+            else xb = make_uint4(0, 0, 0, 0);
+          }
+          if (mode & 4) {
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+r"(acc[i][0]), "+r"(acc[i][1]), "+r"(acc[i][2]), "+r"(acc[i][3])
+                         : "r"(wv.x), "r"(wv.x & 0xf0f0f0f0u), "r"(wv.y), "r"(wv.y & 0xf0f0f0f0u), "r"(xb.x), "r"(xb.y));
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+r"(acc[(i + 2) & 3][0]), "+r"(acc[(i + 2) & 3][1]), "+r"(acc[(i + 2) & 3][2]), "+r"(acc[(i + 2) & 3][3])
+                         : "r"(wv.z), "r"(wv.z & 0xf0f0f0f0u), "r"(wv.w), "r"(wv.w & 0xf0f0f0f0u), "r"(xb.z), "r"(xb.w));
+          } else {
+            acc[i][0] += (int)(wv.x ^ wv.y ^ wv.z ^ wv.w ^ xb.x ^ xb.y ^ xb.z ^ xb.w);
+          }
+        }
+      }
+    }
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  int sink = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) sink += acc[c][0] + acc[c][1] + acc[c][2] + acc[c][3];
+  if (tid == 0) { out[0] = (unsigned long long)(t1 - t0); out[1] = (unsigned long long)(uint32_t)sink; }
+}
+
+extern "C" int b2l_debug_consumer_rate(void* out, int warps, int iters, int mode, int n_ctas, b2l_stream_t stream) {
+  B2L_CHECK_ARG(out && (warps == 8 || warps == 16) && iters > 0 && n_ctas > 0, "b2l_debug_consumer_rate: bad argument");
+  const int smem = 8 * 16384 + 4 * (4096 + 64) + 16;
+  B2L_CUDA(cudaFuncSetAttribute(consumer_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  consumer_rate_kernel<<<n_ctas, warps * 32, smem, (cudaStream_t)stream>>>((unsigned long long*)out, iters, mode);
+  B2L_LAUNCH_CHECK("consumer_rate_kernel");
+  return 0;
+}
+
 // ---- what does a grid-wide dependency cost without a kernel boundary?  Every CTA (all co-resident) arrives on a
 // global counter with red.release and polls it with ld.acquire until all have arrived; out[r] = max over CTAs of
 // the nanoseconds between its arrival and its release, out[rounds + r] = min.  The persistent-kernel plan of

@@ -91,6 +91,13 @@ __device__ __forceinline__ void kblock_imma(int (&acc)[MAX_HALVES][2][4], const 
   }
 }
 
+// One tile (16 rows x 64 k) into one accumulator set.
+__device__ __forceinline__ void single_imma(int (&a)[2][4], const uint8_t* tile, const uint4& xb) {
+  const uint4 wv = *reinterpret_cast<const uint4*>(tile);
+  mma_u8s8_16832(a[0], wv.x, wv.x & 0xf0f0f0f0u, wv.y, wv.y & 0xf0f0f0f0u, xb.x, xb.y);
+  mma_u8s8_16832(a[1], wv.z, wv.z & 0xf0f0f0f0u, wv.w, wv.w & 0xf0f0f0f0u, xb.z, xb.w);
+}
+
 // MAXC = activation chunks (2048 elements each) a thread block caches in registers during the prologue:
 // 6 covers K <= 12288 (every 7B/13B/30B layer), 12 covers K <= 24576 (65B mlp.c_proj, K = 22016).
 // NDIG = base-256 digits of the scaled activations: 4 (|X| < 2^30) or 3 (|X| < 2^22; wide K, smaller planes).
@@ -101,12 +108,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_kb = p.K / KB;                                              // k blocks per 16-row block
-  const int stages_per_unit = (n_kb + KBP_PER_STAGE - 1) / KBP_PER_STAGE;  // the last stage of a unit may be short
+  // A 16 KB stage holds 32 tiles of 512 B: 16 k-block positions of BOTH 16-row blocks of a pair, or 32 positions
+  // of a single block (the ring slot is always used in full).  The last stage of a unit may be short.
+  const int spu2 = (n_kb + KBP_PER_STAGE - 1) / KBP_PER_STAGE, spu1 = (n_kb + 2 * KBP_PER_STAGE - 1) / (2 * KBP_PER_STAGE);
   // this CTA's contiguous range of 16-row blocks, processed as pairs and at most one single
   const int rb_lo = (int)(((long long)blockIdx.x * p.n_rb) / gridDim.x);
   const int rb_hi = (int)(((long long)(blockIdx.x + 1) * p.n_rb) / gridDim.x);
   const int n_units = (rb_hi - rb_lo + 1) / 2;
-  const int total_stages = n_units * stages_per_unit;
+  const int total_stages = ((rb_hi - rb_lo) / 2) * spu2 + ((rb_hi - rb_lo) & 1) * spu1;
   const uint32_t bar_full = sbase + L.bars, bar_empty = bar_full + MAX_STAGES * 8;
   const uint32_t PS = plane_stride(p.K);
 
@@ -131,14 +140,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
         const int rb = rb_lo + 2 * u;
         const int halves = min(2, rb_hi - rb);
         const uint8_t* src = p.qwt + (size_t)rb * n_kb * KB_BYTES;
-        for (int s = 0; s < stages_per_unit; ++s, ++it) {
-          const int nkb = min(KBP_PER_STAGE, n_kb - s * KBP_PER_STAGE);
+        const int per_stage = halves == 2 ? KBP_PER_STAGE : 2 * KBP_PER_STAGE;
+        for (int kb0 = 0; kb0 < n_kb; kb0 += per_stage, ++it) {
+          const int nkb = min(per_stage, n_kb - kb0);
           const uint32_t bytes = (uint32_t)nkb * KB_BYTES;
           mbar_wait(bar_empty + slot * 8, phase);
           mbar_expect_tx(bar_full + slot * 8, bytes * halves);
           for (int h = 0; h < halves; ++h)
             tma_bulk_g2s(sbase + L.ring + slot * STAGE_BYTES + h * HALF_STAGE_BYTES,
-                         src + ((size_t)h * n_kb + (size_t)s * KBP_PER_STAGE) * KB_BYTES, bytes, bar_full + slot * 8);
+                         src + ((size_t)h * n_kb + kb0) * KB_BYTES, bytes, bar_full + slot * 8);
           if (++slot == p.nst) { slot = 0; phase ^= 1; }
           if (it + 1 == min(total_stages, p.nst)) pdl_launch_dependents();  // ring full: next kernel may prefetch
         }
@@ -284,35 +294,43 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int i = 0; i < 4; ++i) acc[h][c][i] = 0;
-      for (int s = 0; s < stages_per_unit; ++s) {
-        const int nkb = min(KBP_PER_STAGE, n_kb - s * KBP_PER_STAGE);
+      const int per_stage = halves == 2 ? KBP_PER_STAGE : 2 * KBP_PER_STAGE;
+      for (int kb0 = 0; kb0 < n_kb; kb0 += per_stage) {
+        const int nkb = min(per_stage, n_kb - kb0);
         mbar_wait(bar_full + slot * 8, phase);
+        // warp w owns tiles w, w + 8, w + 16, w + 24 of the stage (same addresses for pairs and singles):
+        // a pair: k-block positions w, w + 8 of block 0 and of block 1 (the digit fragments are shared);
+        // a single: positions w, w + 8, w + 16, w + 24 of the one block, accumulated in both accumulator sets
         const uint8_t* st_base = smem + L.ring + slot * STAGE_BYTES + lane * 16;
-        if (nkb == KBP_PER_STAGE && !p.nocompute) {
-          // the common case (full stage), branch-free for two halves and for one
+        const uint8_t* xq = xf_lane + kb0 * xf_step;
+        if (!p.nocompute) {
           if (halves == MAX_HALVES) {
+            if (nkb == KBP_PER_STAGE) {
 #pragma unroll
-            for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
-              const int kbl = i * NCW + warp;
-              const uint4 xb = *reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * xf_step);
-              kblock_imma<MAX_HALVES>(acc, st_base + kbl * KB_BYTES, xb);
+              for (int i = 0; i < 2; ++i) {
+                const int kbl = i * NCW + warp;
+                kblock_imma<MAX_HALVES>(acc, st_base + kbl * KB_BYTES, *reinterpret_cast<const uint4*>(xq + kbl * xf_step));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const int kbl = i * NCW + warp;
+                if (kbl < nkb) kblock_imma<MAX_HALVES>(acc, st_base + kbl * KB_BYTES, *reinterpret_cast<const uint4*>(xq + kbl * xf_step));
+              }
             }
           } else {
+            if (nkb == 2 * KBP_PER_STAGE) {
 #pragma unroll
-            for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
-              const int kbl = i * NCW + warp;
-              const uint4 xb = *reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * xf_step);
-              kblock_imma<1>(acc, st_base + kbl * KB_BYTES, xb);
-            }
-          }
-        } else if (!p.nocompute) {
+              for (int i = 0; i < 4; ++i) {
+                const int kbl = i * NCW + warp;
+                single_imma(acc[i & 1], st_base + kbl * KB_BYTES, *reinterpret_cast<const uint4*>(xq + kbl * xf_step));
+              }
+            } else {
 #pragma unroll
-          for (int i = 0; i < KBP_PER_STAGE / NCW; ++i) {
-            const int kbl = i * NCW + warp;  // k-block position inside the stage
-            if (kbl < nkb) {
-              const uint4 xb = *reinterpret_cast<const uint4*>(xf_lane + (s * KBP_PER_STAGE + kbl) * xf_step);
-              if (halves == MAX_HALVES) kblock_imma<MAX_HALVES>(acc, st_base + kbl * KB_BYTES, xb);
-              else kblock_imma<1>(acc, st_base + kbl * KB_BYTES, xb);
+              for (int i = 0; i < 4; ++i) {
+                const int kbl = i * NCW + warp;
+                if (kbl < nkb) single_imma(acc[i & 1], st_base + kbl * KB_BYTES, *reinterpret_cast<const uint4*>(xq + kbl * xf_step));
+              }
             }
           }
         }
@@ -325,6 +343,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
       const int buf = u & 1;
       named_bar_sync(4 + buf, NCW * 32 + 32);  // the epilogue warp has drained this scratch buffer (two units ago)
       if (t4 < 2) {
+        if (halves != MAX_HALVES) {   // a single block: its two accumulator sets hold different k-block positions
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[0][c][i] += acc[1][c][i];
+        }
 #pragma unroll
         for (int h = 0; h < MAX_HALVES; ++h) {
           const int c0 = acc[h][0][0] + acc[h][1][0], c1 = acc[h][0][1] + acc[h][1][1];
@@ -475,7 +499,9 @@ template <int MAXC, int NDIG>
 int launch_gemv(const Params& p0, int ctas_per_sm, int grid_override, bool pdl, cudaStream_t stream) {
   Params p = p0;
   // ring: as deep as fits `ctas_per_sm` CTAs per SM
-  const uint32_t budget = (ctas_per_sm >= 2 ? 110u : 224u) * 1024u;
+  // B2L_GEMV_SMEM_KB: shared-memory budget of a CTA (default: 110 KB for two CTAs per SM, 224 KB for one)
+  static const int env_kb = [] { const char* e = getenv("B2L_GEMV_SMEM_KB"); return e ? atoi(e) : 0; }();
+  const uint32_t budget = (env_kb > 0 ? (uint32_t)env_kb : (ctas_per_sm >= 2 ? 110u : 224u)) * 1024u;
   const uint32_t fixed = smem_layout(0, p.K, NDIG).total;
   int nst = fixed + 2 * STAGE_BYTES <= budget ? (int)((budget - fixed) / STAGE_BYTES) : 0;
   if (nst > MAX_STAGES) nst = MAX_STAGES;

@@ -14,7 +14,7 @@ constexpr int KBP_PER_STAGE = 16;             // k-block positions per stage (2 
 constexpr int MAX_HALVES = 2;                 // a unit is one or two consecutive 16-row blocks sharing the B fragments
 constexpr int HALF_STAGE_BYTES = KBP_PER_STAGE * KB_BYTES;   // 8 KB
 constexpr int STAGE_BYTES = MAX_HALVES * HALF_STAGE_BYTES;   // 16 KB
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 13;
 constexpr int PRODUCER_WARP = NCW;            // warp 8
 constexpr int NTHREADS = (NCW + 2) * 32;      // 320
 

@@ -317,8 +317,10 @@ class LLaMA(nn.Module):
     decode_flags: int = 1
     #: return a fresh logits tensor per call like the reference (False: a view of the static buffer)
     copy_logits: bool = True
-    #: batch-1 decode (head_size 128) runs as one persistent kernel per token (B2L_PERSISTENT=0: one kernel per op)
-    persistent: bool = os.environ.get("B2L_PERSISTENT", "1") != "0"
+    #: batch-1 decode (head_size 128) as ONE persistent kernel per token (csrc/decode_mega.cu) instead of one kernel
+    #: per op.  Opt-in (B2L_PERSISTENT=1): measured on B200 it is correct but slower than the per-op path under
+    #: programmatic dependent launch (1330 vs 964 us per 7B token).
+    persistent: bool = os.environ.get("B2L_PERSISTENT", "0") == "1"
 
     def __init__(self, config: LLaMAConfig) -> None:
         super().__init__()

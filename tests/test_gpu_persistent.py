@@ -1,4 +1,4 @@
-"""-m gpu: the persistent per-token decode kernel (csrc/decode_mega.cu) against the CPU oracle and against the
+"""-m gpu: the persistent per-token decode kernel (csrc/decode_mega.cu, opt-in) against the CPU oracle and against the
 one-kernel-per-op path, on head_size-128 models small enough for the oracle: short and deep positions (1, 2 and 3
 attention splits), a full cache, the roll branch (model.py:214-218), graph replay, and the kernel's own error word."""
 import pytest
@@ -40,10 +40,11 @@ def _decode(model, oracle, dev, prompt, S, steps, seed=0):
     return got, want
 
 
-def test_persistent_kernel_is_the_default_decode_path(dev):
+def test_persistent_kernel_decode_path(dev):
     from gpu_util import build_tiny
 
     model, oracle, _ = build_tiny(dev, CFG, seed=3, exact_linears=True)
+    model.persistent = True
     prompt = torch.tensor([[3, 17, 40, 41, 2, 77]])
     got, want = _decode(model, oracle, dev, prompt, 64, 8)
     st = model._decode
@@ -67,6 +68,7 @@ def test_persistent_deep_context_and_roll_vs_oracle_and_per_op_path(dev, S, T0, 
     torch.manual_seed(S + T0)
     prompt = torch.randint(0, CFG["vocab_size"], (1, T0))
     model, oracle, _ = build_tiny(dev, CFG, seed=5, exact_linears=True)
+    model.persistent = True
     got, want = _decode(model, oracle, dev, prompt, S, steps, seed=1)
     assert model._decode.plan is not None
     model._decode.check()
@@ -94,6 +96,7 @@ def test_persistent_greedy_generate_equals_oracle_tokens(dev):
     from gpu_util import build_tiny
 
     model, oracle, _ = build_tiny(dev, CFG, seed=9)
+    model.persistent = True
     prompt = torch.tensor([5, 100, 319, 7, 48, 1, 250], dtype=torch.int32)
     y = P.generate(model, prompt.to(dev), 40, top_k=1)
     want = O.generate(oracle, prompt, 40, top_k=1)

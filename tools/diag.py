@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "grid_flag", "hmma_rate", "imma_rate", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "grid_flag", "hmma_rate", "imma_rate", "consumer_rate", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline", "mega_timeline"]
 
 
 _DLIB = None
@@ -28,7 +28,8 @@ def dlib():
         vp, ci = C.c_void_p, C.c_int
         for name, args in {"b2l_debug_mma_rate": [vp, ci, ci, ci, ci, vp], "b2l_debug_mma_issuers": [vp, ci, ci, vp],
                            "b2l_debug_grid_flag": [vp, vp, ci, ci, vp], "b2l_debug_hmma_rate": [vp, ci, ci, ci, ci, vp],
-                           "b2l_debug_imma_rate": [vp, ci, ci, ci, ci, vp]}.items():
+                           "b2l_debug_imma_rate": [vp, ci, ci, ci, ci, vp],
+                           "b2l_debug_consumer_rate": [vp, ci, ci, ci, ci, vp]}.items():
             getattr(h, name).restype = ci
             getattr(h, name).argtypes = args
         h.b2l_diag_last_error.restype = C.c_char_p
@@ -605,6 +606,27 @@ def sec_imma_rate():
                       f"{cyc / per_smsp:.2f} clk per MMA per sub-partition", flush=True)
 
 
+def sec_consumer_rate():
+    """The decode consumer loop on shared-memory-resident stages: what bounds it -- LDS, IMMA issue, or their sum?"""
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    out = torch.zeros(2, dtype=torch.int64, device=dev)
+    iters = 200
+    names = {1: "weights LDS", 2: "digit LDS", 3: "both LDS", 4: "IMMA only", 5: "weights LDS + IMMA", 7: "all", 15: "all, unused lanes predicated off",
+             13: "weights LDS + IMMA + (digits off)"}
+    for warps in (16, 8):
+        for ctas in (1, 148):
+            for mode in (1, 2, 3, 4, 5, 7, 15):
+                for _ in range(2):
+                    dcheck(dlib().b2l_debug_consumer_rate(out.data_ptr(), warps, iters, mode, ctas, L.stream_ptr()), "consumer_rate")
+                    torch.cuda.synchronize()
+                cyc = int(out[0]) / (iters * 8)
+                print(f"warps={warps:2d} ctas={ctas:3d} mode={mode:2d} ({names.get(mode, '')}): {cyc:.0f} cycles per 16 KB stage  "
+                      f"-> {16384 / cyc:.1f} B/clk/SM = {16384 / cyc * 1.965 * 148 / 1e3:.1f} TB/s-equivalent", flush=True)
+
+
 def sec_trace():
     """clock64 stamps of CTA 0 of one launch: where does a CTA spend its time?"""
     import torch
@@ -911,6 +933,54 @@ def sec_timeline():
             tot = int(t[n - 1, 4]) - int(t[0, 0])
             print(f"  whole step (first start -> lm_head end): {tot / 1e3:.1f} us; layer 4 start -> layer 5 start: "
                   f"{(int(t[25, 0]) - int(t[20, 0])) / 1e3:.2f} us")
+
+
+def sec_mega_timeline():
+    """Per-op %globaltimer stamps of the persistent decode kernel (7B, one eager step): where does an op's time go?"""
+    import torch
+    from bench import build_synthetic_model
+
+    dev = torch.device("cuda")
+    model = build_synthetic_model("7B", dev)
+    S = 2048
+    model.graph_after = 0
+    model.copy_logits = False
+    pos0 = int(os.environ.get("B2L_TL_POS", "64"))
+    with torch.no_grad():
+        model(torch.randint(0, 32000, (1, 16), device=dev, dtype=torch.int32), S, torch.arange(16, device=dev))
+        tok = torch.randint(0, 32000, (1, 1), device=dev, dtype=torch.int32)
+        for i in range(3):
+            model(tok, S, torch.tensor([pos0 + i], device=dev))
+        st = model._decode
+        assert st.plan is not None
+        n = 5 * model.config.n_layer + 1
+        tl = torch.zeros((n, 16), dtype=torch.int64, device=dev)
+        tl[:, 5] = 2**62
+        st.args.timeline = tl.data_ptr()
+        model(tok, S, torch.tensor([pos0 + 3], device=dev))
+        torch.cuda.synchronize()
+        st.args.timeline = None
+        st.check()
+    t = tl.cpu()
+    names = ["c_attn", "attn", "c_proj", "fc12", "mlp_proj"]
+    base = int(t[20, 5])
+    print(f"pos={pos0 + 3}; ns relative to layer 4 c_attn's first flag-seen: flag seen (min over CTAs) | CTA0 flag seen | CTA0 digits ready | "
+          "CTA0 loop done | loop done (max) | arrive (max)")
+    for li in range(20, 31):
+        v = [int(t[li, k]) for k in (5, 0, 1, 2, 3, 4)]
+        r = [x - base if x not in (0, 2**62) else None for x in v]
+        print(f"  L{li // 5} {names[li % 5]:9s} {r}   CTA0: consumer waited {int(t[li, 6]) / 1.965:.0f} ns for full stages, producer waited {int(t[li, 7]) / 1.965:.0f} ns for empty slots; "
+              f"units {int(t[li, 12])}, loop {int(t[li, 9]) / 1.965:.0f} ns of which scratch-free barrier {int(t[li, 8]) / 1.965:.0f} ns; epilogue warp {int(t[li, 11]) / 1.965:.0f} ns "
+              f"of which waiting for partials {int(t[li, 10]) / 1.965:.0f} ns")
+    print(f"  layer 4 -> layer 5 (flag seen min): {(int(t[25, 5]) - int(t[20, 5])) / 1e3:.2f} us;  whole step: "
+          f"{(int(t[n - 1, 4]) - int(t[0, 0])) / 1e3:.1f} us")
+    per = {}
+    for li in range(5, n - 1):
+        a, b = int(t[li, 5]), int(t[li + 1, 5])
+        per.setdefault(names[li % 5], []).append((b - a) / 1e3)
+    for k, v in per.items():
+        v = sorted(v)
+        print(f"  {k:9s}: flag-seen to next flag-seen us: median {v[len(v) // 2]:.2f} min {v[0]:.2f} max {v[-1]:.2f}")
 
 
 def sec_precision():
