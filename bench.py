@@ -2,20 +2,24 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A step = one decoded token (one pass of generate()'s loop body, generate.py:63-89:
-model forward + top-k/softmax/multinomial sampling) on random-init 7B gptq.int4
-weights, KV cache S = 2048.  Prints ONE JSON line (rank 0).  See DESIGN.md section
-"Measurement" for what every field means.
+A step = one decoded token (one pass of generate()'s loop body, generate.py:63-89: model forward + top-k / softmax /
+multinomial sampling) on random-init 7B gptq.int4 weights, KV cache S = 2048.  The K timed steps are spread EVENLY over
+positions 16..2047 whatever K is (a stride, not consecutive positions), so `value` is a true ctx-2048 mean;
+`config.points` adds tokens/s at fixed positions 128, 1024 and 2047.  Prints ONE JSON line (rank 0).
 
   value     tokens/s, device-timed (CUDA events), inputs resident in HBM, no host sync
-  e2e       same loop driven from HOST buffers: per step a pinned H2D copy of the token
-            and position, and a D2H read of the sampled token
-  roofline  the tcgen05 int4 linear kernel: algorithmic bytes of all its launches in one
-            token / their summed duration, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline / --impl reference: the oracle port of the reference CPU path
-            (dense dequant + F.linear per call, quantization.py:392-423) on host cores
-N > 1: independent replicas, one process per GPU (the reference has no multi-GPU
-inference); weak scaling, no data-path collective.
+  e2e       same loop driven from HOST buffers: per step a pinned H2D copy of the token and position, and a D2H read
+            of the sampled token
+  roofline  the dominant kernel, q4_gemv_kernel (exact int8-digit MMA): algorithmic bytes of all its launches in one
+            token / their summed duration, against MEASURED_PEAKS.json hbm_gbs; whole_token_* = the same for the full
+            step (weights + KV bytes of the timed positions) from `value`
+  cpu_baseline / --impl reference: the UNMODIFIED reference model (lit_llama.model.LLaMA under
+            quantization("gptq.int4"), installed from the reference checkout into oracle/_ref by
+            __graft_entry__.build()) on the host cores, same synthetic weights as the GPU arm, whole tokens through
+            all 32 Blocks; the token loop is the golden-pinned restatement of generate.py (oracle/llama_oracle.py).
+            Fallback when oracle/_ref is absent: the oracle port (kind "port").
+N > 1: independent replicas, one process per GPU (the reference has no multi-GPU inference, SURVEY.md section 2.1);
+weak scaling, no data-path collective.  The tensor-parallel path is measured by tools/tp_bench.py.
 """
 import argparse
 import json
@@ -34,28 +38,67 @@ PROMPT_T = 16
 TOP_K, TEMPERATURE = 200, 0.8  # generate.py:99-100 defaults
 
 
-def model_bytes(cfg_name: str):
-    """Algorithmic bytes of SURVEY.md section 8d for batch 1: W and KV bytes per position."""
-    from oracle.llama_oracle import CONFIGS, n_hidden_for
+LLAMA_SHAPES = {"7B": (32, 32, 4096), "13B": (40, 40, 5120), "30B": (60, 52, 6656), "65B": (80, 64, 8192)}  # model.py:43-48
 
-    c = CONFIGS[cfg_name]
-    C, L = c["n_embd"], c["n_layer"]
+
+def n_hidden_for(n_embd: int) -> int:
+    """model.py:243-245: find_multiple(int(2 * 4 * n_embd / 3), 256)."""
+    h = int(2 * 4 * n_embd / 3)
+    return h if h % 256 == 0 else h + 256 - h % 256
+
+
+def model_bytes(cfg_name: str):
+    """Algorithmic bytes of SURVEY.md section 8d for batch 1: W (packed int4 linears incl. lm_head, bf16 scales and
+    zeros, RMSNorm scales, one wte row) and KV bytes per position."""
+    L, _, C = LLAMA_SHAPES[cfg_name]
     nh, V = n_hidden_for(C), 32000
     lin_params = L * (3 * C * C + C * C + 3 * C * nh) + V * C
     lin_rows = L * (3 * C + C + 2 * nh + C) + V
-    W = lin_params // 2 + lin_rows * 2 * 2 + (2 * L + 1) * C * 2 + C * 2  # packed + scales/zeros bf16 + norms + 1 wte row
+    W = lin_params // 2 + lin_rows * 2 * 2 + (2 * L + 1) * C * 2 + C * 2
     kv_per_pos = 2 * L * C * 2
     return W, kv_per_pos
 
 
-def build_synthetic_model(name, dev, seed=1234):
-    """Random-init gptq.int4 model of the named size, built directly on the GPU with the
-    direct synthesis of SURVEY.md section 8d (uniform levels, zero 8, per-row scales)."""
+def synth_state(name, seed=1234, dev=None):
+    """Random-init gptq.int4 weights of the named size: the direct synthesis of SURVEY.md section 8d (uniform levels,
+    zero 8, per-row scales).  Drawn with the generator of `dev` (default: cuda:0 when there is one, so that the GPU
+    arm and the CPU reference arm -- which moves the tensors to the host -- hold IDENTICAL weights)."""
+    import torch
+
+    if dev is None:
+        dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    L, _, C = LLAMA_SHAPES[name]
+    nh, V = n_hidden_for(C), 32000
+    g = torch.Generator(device=dev).manual_seed(seed)
+    std = 0.02 / (2 * L) ** 0.5
+    sd = {}
+
+    def lin(prefix, out_f, in_f):
+        sd[prefix + ".quant_weight"] = torch.empty((in_f // 2, out_f), dtype=torch.uint8, device=dev).random_(0, 256, generator=g).t()  # strides (1, out)
+        sd[prefix + ".scales"] = ((0.75 + 0.5 * torch.rand((out_f, 1), generator=g, device=dev)) * (std / 4.61)).to(torch.bfloat16)
+        sd[prefix + ".zeros"] = torch.full((out_f, 1), 8.0, dtype=torch.bfloat16, device=dev)
+
+    sd["transformer.wte.weight"] = (torch.randn((V, C), generator=g, device=dev) * 0.02).to(torch.bfloat16)
+    for i in range(L):
+        p = f"transformer.h.{i}."
+        sd[p + "rms_1.scale"] = torch.ones(C, dtype=torch.bfloat16, device=dev)
+        sd[p + "rms_2.scale"] = torch.ones(C, dtype=torch.bfloat16, device=dev)
+        lin(p + "attn.c_attn", 3 * C, C)
+        lin(p + "attn.c_proj", C, C)
+        lin(p + "mlp.c_fc1", nh, C)
+        lin(p + "mlp.c_fc2", nh, C)
+        lin(p + "mlp.c_proj", C, nh)
+    sd["transformer.ln_f.scale"] = torch.ones(C, dtype=torch.bfloat16, device=dev)
+    lin("lm_head", V, C)
+    return sd
+
+
+def build_synthetic_model(name, dev, seed=1234, state=None):
+    """The B200 model of the named size holding synth_state(name, seed) (same tensors as the CPU reference arm)."""
     import torch
 
     import lit_llama_b200 as P
     from lit_llama_b200.utils import quantization
-    from lit_llama_b200.quantization import ColBlockQuantizedLinear
 
     prev = torch.get_default_dtype()
     torch.set_default_dtype(torch.bfloat16)
@@ -64,17 +107,11 @@ def build_synthetic_model(name, dev, seed=1234):
             model = P.LLaMA.from_name(name)
     finally:
         torch.set_default_dtype(prev)
-    g = torch.Generator(device=dev).manual_seed(seed)
-    std = 0.02 / (2 * model.config.n_layer) ** 0.5
+    sd = state if state is not None else synth_state(name, seed, dev)
     with torch.no_grad():
-        for m in model.modules():
-            if isinstance(m, ColBlockQuantizedLinear):
-                m.quant_weight.random_(0, 256, generator=g)
-                m.zeros.fill_(8.0)
-                m.scales.copy_(((0.75 + 0.5 * torch.rand(m.scales.shape, device=dev, generator=g)) * (std / 4.61)).to(m.scales.dtype))
-            elif isinstance(m, P.RMSNorm):
-                m.scale.fill_(1.0)
-        model.transformer.wte.weight.normal_(0.0, 0.02, generator=g)
+        own = model.state_dict()
+        for k, v in sd.items():
+            own[k].copy_(v)     # in place: keeps the reference strides of quant_weight
     return model.eval()
 
 
@@ -133,76 +170,102 @@ def sample_next(logits, top_k=TOP_K, temperature=TEMPERATURE):
     return torch.multinomial(probs, num_samples=1)
 
 
-def cpu_baseline(n_blocks=4, threads=None):
-    """The reference's CPU path (oracle port) on 7B shapes: one decoded token through
-    `n_blocks` Blocks + lm_head, extrapolated to n_layer Blocks."""
+def host_threads():
+    """Threads for the CPU arm: every core this process may use (torchrun exports OMP_NUM_THREADS=1, which would
+    silently turn the baseline into a single-core run), capped at 32 -- the reference's CPU path is a chain of small
+    torch ops per Linear and runs SLOWER beyond that on a 100+-thread host (measured in round 1: 7.4x swings)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, int(os.environ.get("B2L_CPU_THREADS", "32"))))
+
+
+def reference_model(state):
+    """The UNMODIFIED reference model on the CPU: lit_llama.model.LLaMA built under lit_llama.utils.quantization
+    ("gptq.int4") from oracle/_ref (pip-installed from the reference checkout by __graft_entry__.build(); the three
+    file `lightning` stand-in oracle/_shim satisfies lit_llama/utils.py:15).  None when oracle/_ref is absent."""
+    import torch
+
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "lit_llama")):
+        return None
+    for pth in (os.path.join(ROOT, "oracle", "_shim"), ref_dir):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    from lit_llama.model import LLaMA  # noqa: E402  (the reference's own class)
+    from lit_llama.utils import quantization  # noqa: E402
+
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with quantization("gptq.int4"):
+            model = LLaMA.from_name(MODEL)
+    finally:
+        torch.set_default_dtype(prev)
+    own = model.state_dict()
+    with torch.no_grad():
+        for k, v in state.items():
+            own[k].copy_(v.cpu())
+    return model.eval()
+
+
+def cpu_reference_tokens(n_tokens, budget_s, prompt_t=8):
+    """Decode on the host with the reference's own model code: prefill `prompt_t` tokens (untimed), then whole decoded
+    tokens (all 32 Blocks + lm_head + the reference's sampling ops) until `n_tokens` are done or `budget_s` is spent
+    (always at least one).  Returns the cpu_baseline dict; value = 1 / median seconds per token."""
     import torch
 
     from oracle import llama_oracle as O
 
-    if threads is None:
-        # every host thread this process may use (torchrun exports OMP_NUM_THREADS=1, which would
-        # silently turn the baseline into a single-core run)
-        try:
-            threads = len(os.sched_getaffinity(0))
-        except AttributeError:
-            threads = os.cpu_count() or 1
+    threads = host_threads()
     torch.set_num_threads(threads)
-    c = O.CONFIGS[MODEL]
-    C, nhd, L = c["n_embd"], c["n_head"], c["n_layer"]
-    nh = O.n_hidden_for(C)
-    g = torch.Generator().manual_seed(0)
-
-    def lin(out_f, in_f):
-        qw = torch.randint(0, 256, (in_f // 2, out_f), dtype=torch.uint8, generator=g).t()
-        return O.QLin("gptq", qw=qw, scales=torch.full((out_f, 1), 0.0005, dtype=torch.bfloat16),
-                      zeros=torch.full((out_f, 1), 8.0, dtype=torch.bfloat16), bits=4, tile_cols=in_f)
-
-    layers = [dict(rms_1=torch.ones(C, dtype=torch.bfloat16), rms_2=torch.ones(C, dtype=torch.bfloat16), c_attn=lin(3 * C, C),
-                   c_proj=lin(C, C), c_fc1=lin(nh, C), c_fc2=lin(nh, C), mlp_proj=lin(C, nh)) for _ in range(n_blocks)]
-    m = O.OracleLLaMA(n_layer=n_blocks, n_head=nhd, n_embd=C, block_size=S_CTX, padded_vocab_size=32000,
-                      wte=(torch.randn(32000, C, generator=g) * 0.02).bfloat16(), lm_head=lin(32000, C),
-                      ln_f=torch.ones(C, dtype=torch.bfloat16), layers=layers)
+    state = synth_state(MODEL, 1234)
+    model = reference_model(state)
+    kind = "reference"
+    if model is None:   # oracle/_ref missing (the reference checkout was not available at build time): the pinned port
+        kind = "port"
+        cpu = {k: v.cpu() for k, v in state.items()}
+        L, nh, _ = LLAMA_SHAPES[MODEL]
+        model = O.OracleLLaMA.from_state_dict(cpu, L, nh, S_CTX, "gptq.int4")
+        fwd = model.forward
+    else:
+        fwd = model.__call__
+    del state
+    g = torch.Generator().manual_seed(7)
+    prompt = torch.randint(0, 32000, (1, prompt_t), generator=g)
+    times = []
     with torch.no_grad():
-        m.forward(torch.randint(0, 32000, (1, PROMPT_T), generator=g), S_CTX, torch.arange(PROMPT_T))  # prefill, untimed
-        tok = torch.randint(0, 32000, (1, 1), generator=g)
-        # time the pieces separately so the extrapolation to n_layer Blocks is exact
-        x = m.wte[tok]
-        t0 = time.perf_counter()
-        rope = m.rope.index_select(0, torch.tensor([PROMPT_T]))
-        mask = torch.ones(1, 1, 1, S_CTX, dtype=torch.bool)
-        mask[..., PROMPT_T + 1:] = False
-        for li, lay in enumerate(m.layers):
-            x = x + m._attn(O.rmsnorm(x, lay["rms_1"]), lay, rope, mask, S_CTX, torch.tensor([PROMPT_T]), li)
-            h = O.rmsnorm(x, lay["rms_2"])
-            x = x + lay["mlp_proj"](torch.nn.functional.silu(lay["c_fc1"](h)) * lay["c_fc2"](h))
-        t_blocks = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        logits = m.lm_head(O.rmsnorm(x, m.ln_f))
-        sample_next(logits)
-        t_head = time.perf_counter() - t0
-    t_token = t_blocks / n_blocks * L + t_head
-    return {"value": 1.0 / t_token, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"1 decoded token at pos {PROMPT_T}: {n_blocks} of {L} Blocks timed ({t_blocks:.2f} s) and scaled x{L}/{n_blocks}, "
-                      f"+ ln_f/lm_head/sampling ({t_head:.2f} s); oracle port of the reference CPU path (dense dequant + F.linear per call)",
-            "s_per_token": t_token}
+        logits = fwd(prompt, S_CTX, torch.arange(prompt_t))
+        tok = sample_next(logits)
+        t_start = time.perf_counter()
+        for i in range(max(1, n_tokens)):
+            t0 = time.perf_counter()
+            logits = fwd(tok.view(1, 1), S_CTX, torch.tensor([prompt_t + i]))
+            tok = sample_next(logits)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > budget_s:
+                break
+    times.sort()
+    med = times[len(times) // 2]
+    what = ("unmodified reference model (lit_llama.model.LLaMA under quantization('gptq.int4'), oracle/_ref) " if kind == "reference"
+            else "oracle port of the reference CPU path (oracle/_ref absent) ")
+    return {"value": 1.0 / med, "unit": "tokens/s", "cores": threads, "kind": kind,
+            "sample": f"{len(times)} whole decoded token(s) after a {prompt_t}-token prefill, all {LLAMA_SHAPES[MODEL][0]} Blocks + lm_head + sampling, "
+                      f"median {med:.2f} s (min {times[0]:.2f}, max {times[-1]:.2f}); " + what +
+                      "on the same synthetic weights as the GPU arm; token loop = generate.py:63-89 restated",
+            "s_per_token": med, "tokens": len(times)}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    t0 = time.perf_counter()
-    vals = []
-    for i in range(max(1, args.warmup > 0) + max(1, min(args.steps, 2))):
-        cb = cpu_baseline(n_blocks=2)
-        vals.append(cb)
-        if time.perf_counter() - t0 > 150:
-            break
-    cb = vals[-1]
+    cb = cpu_reference_tokens(n_tokens=max(3, min(args.steps, 4)), budget_s=150.0)
     line = {"impl": "reference", "metric": "LLaMA-7B gptq.int4 decode tokens/sec", "value": cb["value"], "unit": "tokens/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["s_per_token"] * 1e3,
+            "n_gpus": args.gpus, "steps": cb["tokens"], "warmup": 1, "ms_per_step": cb["s_per_token"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "LLaMA-7B gptq.int4 decode batch=1 ctx=2048 (random-init weights)", "where": "host CPU"},
+            "config": {"workload": "LLaMA-7B gptq.int4 decode batch=1 ctx=2048 (random-init weights)", "where": "host CPU",
+                       "positions": "8.. (the CPU path costs the same at every position: it attends over all 2048 slots)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -279,7 +342,7 @@ def aggregate_throughput(world, steps, t_max):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=512)
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -301,11 +364,14 @@ def main():
     warm = max(3, args.warmup)
     K = args.steps
 
-    model = build_synthetic_model(MODEL, dev, seed=1234 + rank)
+    model = build_synthetic_model(MODEL, dev, seed=1234)   # every replica holds the same weights, decodes its own stream
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     prompt = torch.randint(0, 32000, (PROMPT_T,), device=dev, dtype=torch.int32, generator=gen)
-    lo, span = PROMPT_T, S_CTX - PROMPT_T  # decode positions cycle through [16, 2047]
-    pos_all = [torch.tensor([lo + (i % span)], device=dev) for i in range(warm + K)]
+    lo, span = PROMPT_T, S_CTX - PROMPT_T
+    # the K timed positions are spread evenly over [16, 2047] whatever K is (slots in between stay zero rows: the
+    # attention kernel reads them exactly like written ones); warm-up walks the first positions
+    timed_pos = [lo + (i * span) // K for i in range(K)]
+    pos_all = [torch.tensor([lo + (i % span)], device=dev) for i in range(warm)] + [torch.tensor([q], device=dev) for q in timed_pos]
 
     def barrier():
         if world > 1:
@@ -348,7 +414,7 @@ def main():
             barrier()
             t0 = time.perf_counter()
             for i in range(n):
-                h_pos[0] = lo + (i % span)
+                h_pos[0] = lo + ((i * span) // n if phase == "timed" else i)
                 d_tok.copy_(h_tok, non_blocking=True)
                 d_pos.copy_(h_pos, non_blocking=True)
                 nxt = sample_next(model(d_tok.view(1, 1), S_CTX, d_pos))
@@ -358,13 +424,28 @@ def main():
             barrier()
             t_e2e = time.perf_counter() - t0
 
+        # ---- tokens/s at fixed positions: 24 steps each at p = 128, 1024, 2047
+        points = {}
+        for q in (128, 1024, 2047):
+            pq = torch.tensor([q], device=dev)
+            for _ in range(4):
+                tok = sample_next(model(tok.view(1, 1), S_CTX, pq)).to(torch.int32)
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(24):
+                tok = sample_next(model(tok.view(1, 1), S_CTX, pq)).to(torch.int32)
+            p1.record()
+            torch.cuda.synchronize()
+            points[f"p{q}"] = round(24 / (p0.elapsed_time(p1) * 1e-3), 1)
+
         t_q4, n_q4, q4_name = time_q4_launches(model, dev)
 
     t_dev, t_e2e = reduce_max([t_dev, t_e2e], dev)
 
     if rank == 0:
         W, kv = model_bytes(MODEL)
-        mean_p = sum(lo + (i % span) for i in range(warm, warm + K)) / K
+        mean_p = sum(timed_pos) / K
         bytes_per_token = W + kv * (mean_p + 1) + kv
         peaks = {}
         try:
@@ -387,7 +468,8 @@ def main():
             "steps": K, "warmup": warm, "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "LLaMA-7B gptq.int4 decode batch=1 ctx=2048 (random-init weights)", "prompt_tokens": PROMPT_T,
-                       "positions": f"cycle {lo}..{S_CTX - 1}, mean {mean_p:.0f}", "sampling": f"top_k={TOP_K} temperature={TEMPERATURE}",
+                       "positions": f"{K} positions spread evenly over {lo}..{S_CTX - 1} (mean {mean_p:.0f})",
+                       "points": {**points, "unit": "tokens/s at fixed position"}, "sampling": f"top_k={TOP_K} temperature={TEMPERATURE}",
                        "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                        "l2": "weights 3.31 GB per token >> 126 MB L2 (inputs larger than L2)"},
             "clocks": clk,
@@ -396,11 +478,13 @@ def main():
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "kernel": q4_name, "launches_per_token": n_q4, "bytes_per_token_launches": W,
                          "peak_source": which,
-                         "whole_token": {"bytes": bytes_per_token, "achieved": bytes_per_token * K / t_dev / 1e9,
-                                         "frac": bytes_per_token * K / t_dev / 1e9 / peak}},
+                         "whole_token_bytes": bytes_per_token, "whole_token_achieved": bytes_per_token * K / t_dev / 1e9,
+                         "whole_token_frac": bytes_per_token * K / t_dev / 1e9 / peak},
         }
         if not args.no_cpu_baseline and world == 1:
-            cb = cpu_baseline(n_blocks=2)
+            del model
+            torch.cuda.empty_cache()
+            cb = cpu_reference_tokens(n_tokens=1, budget_s=30.0, prompt_t=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -202,13 +202,22 @@ __global__ void kv_unroll_kernel(const __nv_bfloat16* __restrict__ cache, const 
 // RoPE(q), RoPE(k) + in-place KV append, split-S online-softmax attention over the valid
 // slots, and the cross-split merge (last CTA of a head, atomic ticket).
 //
-// grid (B*n_head, n_split), 4 warps.  A warp handles 4 keys per iteration: 8 lanes per key,
-// 16 head dims (32 B) per lane, so a K/V row is read with two 16-byte loads per lane and a
-// score needs 3 shuffles.  Under PDL the CTA prefetches its K/V chunk into L2 before it
-// waits for the c_attn kernel (old cache rows do not depend on the current token).
+// grid (B*n_head, ceil(S / 64)), 8 warps; CTAs beyond the position-dependent split count exit at once.  A CTA owns
+// 64..256 keys of one head (chosen from the position so that ~400 CTAs work) and streams them as 64-key
+// sub-tiles (K 16 KB + V 16 KB) through a two-deep shared-memory ring with TMA bulk copies: the first two
+// sub-tiles are requested BEFORE griddepcontrol.wait (old cache rows do not depend on the current token), the
+// next one as soon as a buffer has been consumed.  A warp handles 4 keys per round: 8 lanes per key, 16 head
+// dims (32 B) per lane, a score needs 3 shuffles.  The new token's key / value never touch the tile: they are
+// rotated, appended to the cache and scored from registers.
+// Round 1 used one 128-key tile per CTA (64 KB, 3 CTAs per SM): at position 2047 its 512 CTAs needed a second
+// wave and 16 partials per head had to be merged (profiles/r01_ncu_attn_decode_fused_kernel.txt: 0.19 of HBM
+// peak); 256 keys per CTA keep every position a single wave (<= 8 x n_head CTAs) with half the partials.
 // ----------------------------------------------------------------------------------
-constexpr int FD_CHUNK = 128;   // keys per CTA
+constexpr int FD_CHUNK = 256;   // most keys per CTA
+constexpr int FD_SUB = 64;      // keys per sub-tile = smallest number of keys per CTA
 constexpr int FD_WARPS = 8;
+constexpr int FD_TARGET_CTAS = 400;  // working CTAs aimed at (148 SMs x 3 resident CTAs = 444 slots: one wave)
+constexpr int WS_CHUNK = FD_SUB;     // workspace sizing granularity (finest split of any kernel that uses it)
 
 __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -220,10 +229,13 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
 }
 
 __device__ __forceinline__ uint32_t fd_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fd_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
-// Dynamic shared memory: K tile [128 rows][128] bf16 (32 KB), V tile (32 KB), merge scratch.
-constexpr int FD_TILE_BYTES = FD_CHUNK * 128 * 2;
-constexpr int FD_SMEM_BYTES = 2 * FD_TILE_BYTES + FD_WARPS * 128 * 4 + 2 * FD_WARPS * 4 + 16;
+// Dynamic shared memory: 2 buffers x (K sub-tile 16 KB + V sub-tile 16 KB), merge scratch, 2 mbarriers.
+constexpr int FD_SUB_BYTES = FD_SUB * 128 * 2;
+constexpr int FD_SMEM_BYTES = 4 * FD_SUB_BYTES + FD_WARPS * 128 * 4 + 2 * FD_WARPS * 4 + 16;
 
 __global__ void __launch_bounds__(FD_WARPS * 32)
     attn_decode_fused_kernel(const __nv_bfloat16* qkv, __nv_bfloat16* __restrict__ k_cache,
@@ -233,12 +245,10 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
                              int n_head, int S, int block_size, int n_split, unsigned long long* tl) {
   constexpr int HS = 128;
   extern __shared__ __align__(128) uint8_t fsm[];
-  __nv_bfloat16* kt = reinterpret_cast<__nv_bfloat16*>(fsm);
-  __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(fsm + FD_TILE_BYTES);
-  float* sm_acc = reinterpret_cast<float*>(fsm + 2 * FD_TILE_BYTES);              // [FD_WARPS][HS]
+  float* sm_acc = reinterpret_cast<float*>(fsm + 4 * FD_SUB_BYTES);                // [FD_WARPS][HS]
   float* sm_m = sm_acc + FD_WARPS * HS;                                            // [FD_WARPS]
   float* sm_l = sm_m + FD_WARPS;                                                   // [FD_WARPS]
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm_l + FD_WARPS);  // 8-byte aligned by construction
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm_l + FD_WARPS);  // 8-byte aligned by construction
   __shared__ int sm_last;
 
   if (threadIdx.x == 0) tl_min(tl, 0);
@@ -252,36 +262,45 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   const long long p = input_pos[0];
   const int w_slot = (int)(p < S ? p : (long long)S - 1);  // logical slot of the new token
   const int L = w_slot + 1;                                 // valid logical slots 0..L-1
-  const int n_active = (L + FD_CHUNK - 1) / FD_CHUNK;
+  // keys per CTA: a multiple of 64 in [64, 256], chosen (identically by every CTA) so that about FD_TARGET_CTAS CTAs
+  // have work: few long chunks would serialise sub-tiles inside a CTA, many short ones would need a second wave
+  // (measured, tools/diag.py bench_ctx: a sub-tile costs a CTA ~0.7 us, the cross-CTA merge ~3 us -- up to 256
+  // keys stay in ONE CTA per head, with no merge at all)
+  const int want_splits = max(1, FD_TARGET_CTAS / (int)gridDim.x);
+  const int chunk = L <= FD_CHUNK ? FD_CHUNK
+                                  : min(FD_CHUNK, max(FD_SUB, FD_SUB * ((L + FD_SUB * want_splits - 1) / (FD_SUB * want_splits))));
+  const int n_active = (L + chunk - 1) / chunk;
   if (sp >= n_active) return;
   const int ring = *ring_start;
-  const int j0 = sp * FD_CHUNK, j1 = min(L, j0 + FD_CHUNK);
+  const int j0 = sp * chunk, j1 = min(L, j0 + chunk);
   const int n_old = min(j1, L - 1) - j0;  // rows written by earlier steps (slot L-1 is written by this one)
+  const int n_sub = (n_old + FD_SUB - 1) / FD_SUB;
+  const bool has_new = (w_slot >= j0 && w_slot < j1);
 
-  // ---- before the dependency: TMA bulk copies of the old K/V rows of this chunk into shared memory
-  const uint32_t bar_a = fd_smem_u32(bar);
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (n_old > 0) {
-      int phys0 = j0 + ring; if (phys0 >= S) phys0 -= S;
-      const int first = min(n_old, S - phys0);  // rows before the ring wraps
-      const uint32_t total = (uint32_t)n_old * HS * 2 * 2;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(total) : "memory");
-      const __nv_bfloat16* ksrc = k_cache + head_base + (size_t)phys0 * HS;
-      const __nv_bfloat16* vsrc = v_cache + head_base + (size_t)phys0 * HS;
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fd_smem_u32(kt)),
-                   "l"(ksrc), "r"((uint32_t)first * HS * 2), "r"(bar_a) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fd_smem_u32(vt)),
-                   "l"(vsrc), "r"((uint32_t)first * HS * 2), "r"(bar_a) : "memory");
-      if (first < n_old) {  // wrapped part starts at physical row 0
-        const uint32_t rest = (uint32_t)(n_old - first) * HS * 2;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fd_smem_u32(kt + (size_t)first * HS)),
-                     "l"(k_cache + head_base), "r"(rest), "r"(bar_a) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fd_smem_u32(vt + (size_t)first * HS)),
-                     "l"(v_cache + head_base), "r"(rest), "r"(bar_a) : "memory");
-      }
+  // sub-tile i -> buffer i & 1: old K rows then old V rows, each possibly in two pieces (the ring wraps)
+  const uint32_t bar0 = fd_smem_u32(bars);
+  auto request = [&](int i) {
+    const int buf = i & 1;
+    const int cnt = min(FD_SUB, n_old - i * FD_SUB);
+    int phys0 = j0 + i * FD_SUB + ring; if (phys0 >= S) phys0 -= S;
+    const int first = min(cnt, S - phys0);  // rows before the ring wraps
+    const uint32_t bar = bar0 + buf * 8;
+    const uint32_t kd = fd_smem_u32(fsm) + buf * 2 * FD_SUB_BYTES, vd = kd + FD_SUB_BYTES;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)cnt * HS * 2 * 2) : "memory");
+    fd_bulk(kd, k_cache + head_base + (size_t)phys0 * HS, (uint32_t)first * HS * 2, bar);
+    fd_bulk(vd, v_cache + head_base + (size_t)phys0 * HS, (uint32_t)first * HS * 2, bar);
+    if (first < cnt) {  // wrapped part starts at physical row 0
+      fd_bulk(kd + first * HS * 2, k_cache + head_base, (uint32_t)(cnt - first) * HS * 2, bar);
+      fd_bulk(vd + first * HS * 2, v_cache + head_base, (uint32_t)(cnt - first) * HS * 2, bar);
     }
+  };
+  // ---- before the dependency: the first two sub-tiles
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (n_sub > 0) request(0);
+    if (n_sub > 1) request(1);
   }
   // the RoPE row of this position is a constant table entry: fetch it before the dependency too
   const long long prow = p < block_size ? p : (long long)block_size - 1;
@@ -295,7 +314,7 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
       cs[4 * i] = t.x; cs[4 * i + 1] = t.y; cs[4 * i + 2] = t.z; cs[4 * i + 3] = t.w;
     }
   }
-  __syncthreads();  // the barrier is initialised before anyone polls it
+  __syncthreads();  // the barriers are initialised before anyone polls them
   pdl_wait();
   if (threadIdx.x == 0) tl_max(tl, 1);
   pdl_launch_dependents();  // attn.c_proj may start streaming its weights
@@ -317,66 +336,86 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
       q[2 * i + 1] = o * scale;
     }
   }
-  // the CTA whose chunk holds the new slot appends k (rotated) and v: to the cache and to its tile
-  if (w_slot >= j0 && w_slot < j1 && warp == 0 && grp == 0) {
+
+  float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  // ---- old rows, sub-tile by sub-tile: warp w takes rows 8 w .. 8 w + 7 (4 keys per round, 8 lanes per key)
+  for (int i = 0; i < n_sub; ++i) {
+    const int buf = i & 1;
+    const int cnt = min(FD_SUB, n_old - i * FD_SUB);
+    {
+      uint32_t ok;
+      const uint32_t par = (uint32_t)(i >> 1) & 1u;
+      do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar0 + buf * 8), "r"(par) : "memory");
+      } while (!ok);
+    }
+    const __nv_bfloat16* kt = reinterpret_cast<const __nv_bfloat16*>(fsm + buf * 2 * FD_SUB_BYTES);
+    const __nv_bfloat16* vt = kt + FD_SUB * HS;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int r = warp * 8 + it * 4 + grp;
+      const bool valid = r < cnt;
+      const int rc = valid ? r : 0;
+      const uint4* kr = reinterpret_cast<const uint4*>(kt + (size_t)rc * HS + d0);
+      const uint4* vr = reinterpret_cast<const uint4*>(vt + (size_t)rc * HS + d0);
+      float kf[16], vf[16];
+      bf16x8_to_f32(kr[0], kf); bf16x8_to_f32(kr[1], kf + 8);
+      float sc = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) sc = fmaf(q[e], kf[e], sc);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+      if (valid) {
+        bf16x8_to_f32(vr[0], vf); bf16x8_to_f32(vr[1], vf + 8);
+        const float mn = fmaxf(m, sc);
+        const float corr = __expf(m - mn), pj = __expf(sc - mn);
+        l = l * corr + pj;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = fmaf(pj, vf[e], acc[e] * corr);
+        m = mn;
+      }
+    }
+    __syncthreads();   // every warp is done with this buffer
+    if (threadIdx.x == 0 && i + 2 < n_sub) request(i + 2);
+  }
+  if (threadIdx.x == 0) tl_max(tl, 2);
+  // ---- the new token: rotate k, append k and v to the cache, score from registers (warp 0, key group 0)
+  if (has_new && warp == 0 && grp == 0) {
     int phys = w_slot + ring; if (phys >= S) phys -= S;
-    float raw[16];
+    float raw[16], kf[16], vf[16];
     bf16x8_to_f32(ld_coherent_u4(qrow + C), raw);
     bf16x8_to_f32(ld_coherent_u4(qrow + C + 8), raw + 8);
     uint32_t out[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float c = cs[2 * i], s_ = cs[2 * i + 1];
-      const float e = __fsub_rn(__fmul_rn(raw[2 * i], c), __fmul_rn(raw[2 * i + 1], s_));
-      const float o = __fadd_rn(__fmul_rn(raw[2 * i + 1], c), __fmul_rn(raw[2 * i], s_));
-      out[i] = (__float_as_uint(rbf(e)) >> 16) | (__float_as_uint(rbf(o)) & 0xffff0000u);
+      kf[2 * i] = rbf(__fsub_rn(__fmul_rn(raw[2 * i], c), __fmul_rn(raw[2 * i + 1], s_)));
+      kf[2 * i + 1] = rbf(__fadd_rn(__fmul_rn(raw[2 * i + 1], c), __fmul_rn(raw[2 * i], s_)));
+      out[i] = (__float_as_uint(kf[2 * i]) >> 16) | (__float_as_uint(kf[2 * i + 1]) & 0xffff0000u);
     }
-    const uint4 ka = make_uint4(out[0], out[1], out[2], out[3]), kb2 = make_uint4(out[4], out[5], out[6], out[7]);
     const uint4 va = ld_coherent_u4(qrow + 2 * C), vb = ld_coherent_u4(qrow + 2 * C + 8);
     uint4* kd = reinterpret_cast<uint4*>(k_cache + head_base + (size_t)phys * HS + d0);
     uint4* vd = reinterpret_cast<uint4*>(v_cache + head_base + (size_t)phys * HS + d0);
-    kd[0] = ka; kd[1] = kb2; vd[0] = va; vd[1] = vb;
-    uint4* ks = reinterpret_cast<uint4*>(kt + (size_t)(w_slot - j0) * HS + d0);
-    uint4* vsm = reinterpret_cast<uint4*>(vt + (size_t)(w_slot - j0) * HS + d0);
-    ks[0] = ka; ks[1] = kb2; vsm[0] = va; vsm[1] = vb;
-  }
-  if (n_old > 0) {  // the bulk copies have landed
-    uint32_t ok;
-    do {
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar_a) : "memory");
-    } while (!ok);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) tl_max(tl, 2);
-
-  float m = -INFINITY, l = 0.f, acc[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  const int nrows = j1 - j0;
-  for (int rr = warp * 4; rr < nrows; rr += FD_WARPS * 4) {  // warp-uniform trip count; 8 lanes per key
-    const int r = rr + grp;
-    const bool valid = r < nrows;
-    const int rc = valid ? r : nrows - 1;
-    const uint4* kr = reinterpret_cast<const uint4*>(kt + (size_t)rc * HS + d0);
-    const uint4* vr = reinterpret_cast<const uint4*>(vt + (size_t)rc * HS + d0);
-    float kf[16], vf[16];
-    bf16x8_to_f32(kr[0], kf); bf16x8_to_f32(kr[1], kf + 8);
+    kd[0] = make_uint4(out[0], out[1], out[2], out[3]); kd[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    vd[0] = va; vd[1] = vb;
+    bf16x8_to_f32(va, vf); bf16x8_to_f32(vb, vf + 8);
     float sc = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sc = fmaf(q[i], kf[i], sc);
-    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-    if (valid) {
-      bf16x8_to_f32(vr[0], vf); bf16x8_to_f32(vr[1], vf + 8);
-      const float mn = fmaxf(m, sc);
-      const float corr = __expf(m - mn), pj = __expf(sc - mn);
-      l = l * corr + pj;
+    for (int e = 0; e < 16; ++e) sc = fmaf(q[e], kf[e], sc);
+    sc += __shfl_xor_sync(0x000000ffu, sc, 1);
+    sc += __shfl_xor_sync(0x000000ffu, sc, 2);
+    sc += __shfl_xor_sync(0x000000ffu, sc, 4);
+    const float mn = fmaxf(m, sc);
+    const float corr = __expf(m - mn), pj = __expf(sc - mn);
+    l = l * corr + pj;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = fmaf(pj, vf[i], acc[i] * corr);
-      m = mn;
-    }
+    for (int e = 0; e < 16; ++e) acc[e] = fmaf(pj, vf[e], acc[e] * corr);
+    m = mn;
   }
+  __syncwarp();
   if (threadIdx.x == 0) tl_max(tl, 3);
   // merge the 4 key groups of the warp (lanes with the same `sub` hold the same dims)
 #pragma unroll
@@ -433,13 +472,13 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   }
   __syncthreads();  // thread 0's acquire + this barrier order the other CTAs' partials before the loads below
   if (!sm_last) return;
-  // merge: every load is issued before the first use (n_split <= 16 for S <= 2048; larger S loops in batches)
+  // merge: every load is issued before the first use (n_split <= 8 for S <= 2048; larger S loops in batches)
   const float* base = work + (size_t)bh * n_split * (HS + 2);
   float MM = -INFINITY, LL = 0.f, aa = 0.f;
-  for (int s0 = 0; s0 < n_active; s0 += 16) {
-    float ms[16], ls[16], as[16];
+  for (int s0 = 0; s0 < n_active; s0 += 8) {
+    float ms[8], ls[8], as[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const int s2 = s0 + i;
       const bool ok = s2 < n_active;
       const float* bp = base + (size_t)(ok ? s2 : s0) * (HS + 2);
@@ -449,11 +488,11 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
     }
     float bm = MM;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) bm = fmaxf(bm, ms[i]);
+    for (int i = 0; i < 8; ++i) bm = fmaxf(bm, ms[i]);
     const float c0 = (MM == -INFINITY) ? 0.f : __expf(MM - bm);
     LL *= c0; aa *= c0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const float wg = (ms[i] == -INFINITY) ? 0.f : __expf(ms[i] - bm);
       LL += ls[i] * wg;
       aa += as[i] * wg;
@@ -496,7 +535,7 @@ static inline size_t ws_partials_bytes(int B, int n_head, int head_size, int T, 
   int n_split, chunk;
   split_plan(T, S, &n_split, &chunk);
   size_t a = (size_t)B * n_head * T * n_split * (head_size + 2) * sizeof(float);
-  size_t f = (size_t)B * n_head * ((S + FD_CHUNK - 1) / FD_CHUNK) * (head_size + 2) * sizeof(float);
+  size_t f = (size_t)B * n_head * ((S + WS_CHUNK - 1) / WS_CHUNK) * (head_size + 2) * sizeof(float);
   return ((a > f ? a : f) + 15) & ~(size_t)15;
 }
 
@@ -523,7 +562,7 @@ extern "C" int b2l_attention(void* qkv, void* k_cache, void* v_cache, const void
                       "b2l_attention: head_size %d unsupported (even, <= %d)", head_size, 32 * ATT_MAX_EPL);
   cudaStream_t st = (cudaStream_t)stream;
   if (T == 1 && head_size == 128 && !(flags & B2L_F_ROPE_ROWS) && !(flags & B2L_F_ATTN_UNFUSED)) {
-    const int n_split = (S + FD_CHUNK - 1) / FD_CHUNK;
+    const int n_split = (S + FD_SUB - 1) / FD_SUB;
     int* tickets = reinterpret_cast<int*>(reinterpret_cast<char*>(work) + ws_partials_bytes(B, n_head, head_size, T, S));
     static DynSmemCache smem_cache;
     if (int rc = ensure_dyn_smem(attn_decode_fused_kernel, FD_SMEM_BYTES, smem_cache)) return rc;

@@ -209,6 +209,61 @@ def test_fused_attention_equals_unfused(dev, S, cases):
         torch.testing.assert_close(yf.float(), yu.float(), rtol=2 ** -7, atol=2e-3)
 
 
+@pytest.mark.parametrize("B", [1, 8])
+def test_fused_attention_vs_oracle_hs128(dev, B):
+    """The kernel on the benched path (fused rope + KV append + split-S attention + merge, head_size 128) directly
+    against the oracle's restatement of model.py:197-230 (O.rope_apply + index_copy / roll + O.sdpa): positions 0,
+    127, 128 (split boundary of the persistent kernel), 255, 256 (split boundary of this kernel), 1023, 2047 (full
+    cache, 8 splits), and two roll states (model.py:214-218: position >= S with different ring offsets)."""
+    from lit_llama_b200 import _lib as L
+
+    nh, hs, S, blk = 4, 128, 2048, 4096
+    C = nh * hs
+    lib = L.lib()
+    g = torch.Generator(device=dev).manual_seed(17 + B)
+    rope = O.rope_table(blk, hs)
+    rope_d = rope.to(dev)
+    kc = (torch.randn(B, nh, S, hs, device=dev, generator=g) * 0.5).bfloat16()
+    vc = (torch.randn(B, nh, S, hs, device=dev, generator=g) * 0.5).bfloat16()
+    for pos, ring0 in [(0, 0), (127, 0), (128, 0), (255, 0), (256, 0), (1023, 0), (2047, 0), (2048, 0), (3000, 777)]:
+        qkv = torch.randn(B, 1, 3 * C, device=dev, generator=g).bfloat16()
+        k1, v1 = kc.clone(), vc.clone()
+        ring = torch.tensor([ring0], dtype=torch.int32, device=dev)
+        p = torch.tensor([pos], dtype=torch.int64, device=dev)
+        L.check(lib.b2l_ring_advance(p.data_ptr(), 1, ring.data_ptr(), S, L.stream_ptr()), "ring")
+        work = torch.zeros(lib.b2l_attn_workspace_bytes(B, nh, hs, 1, S) // 4 + 1, device=dev, dtype=torch.float32)
+        y = torch.empty(B, 1, C, device=dev, dtype=torch.bfloat16)
+        rc = lib.b2l_attention(qkv.clone().data_ptr(), k1.data_ptr(), v1.data_ptr(), rope_d.data_ptr(), p.data_ptr(), ring.data_ptr(),
+                               y.data_ptr(), work.data_ptr(), B, 1, nh, hs, S, blk, 0, L.stream_ptr())
+        assert rc == 0, lib.b2l_last_error()
+        torch.cuda.synchronize()
+        # ---- oracle on the logical cache
+        kl = torch.roll(kc.cpu(), -ring0, dims=2)   # logical slot j = physical (j + ring0) % S
+        vl = torch.roll(vc.cpu(), -ring0, dims=2)
+        q, k, v = qkv.cpu().split(C, dim=2)
+        rows = rope[pos : pos + 1]
+        q = O.rope_apply(q.view(B, 1, nh, hs), rows).transpose(1, 2)
+        k = O.rope_apply(k.view(B, 1, nh, hs), rows).transpose(1, 2)
+        v = v.view(B, 1, nh, hs).transpose(1, 2)
+        slot = pos
+        if pos >= S:   # model.py:214-218
+            slot = S - 1
+            kl, vl = torch.roll(kl, -1, dims=2), torch.roll(vl, -1, dims=2)
+        kl = kl.index_copy(2, torch.tensor([slot]), k)
+        vl = vl.index_copy(2, torch.tensor([slot]), v)
+        mask = (torch.arange(S) <= slot).view(1, 1, 1, S)
+        want = O.sdpa(q, kl, vl, mask).transpose(1, 2).reshape(B, 1, C)
+        got = y.cpu()
+        err = (got.float() - want.float()).norm() / want.float().norm()
+        assert err < 4e-3, (pos, ring0, float(err))   # fp32 softmax in a different summation order + one bf16 rounding (2^-9)
+        torch.testing.assert_close(got.float(), want.float(), rtol=2 ** -7, atol=2e-3)
+        # the appended row sits in the physical slot the ring assigns, bit-identical to the reference arithmetic
+        ring_now = int(ring)
+        assert ring_now == (ring0 + (1 if pos >= S else 0)) % S
+        phys = (slot + ring_now) % S
+        assert torch.equal(k1[:, :, phys].cpu(), k[:, :, 0]) and torch.equal(v1[:, :, phys].cpu(), v[:, :, 0]), (pos, ring0)
+
+
 def test_batched_decode_rows_are_independent(dev):
     from gpu_util import build_tiny
 
