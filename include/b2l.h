@@ -124,6 +124,13 @@ enum {
  * (model.py:166-167, 252). */
 int b2l_q4_linear_tc(const b2l_q4_linear_args* args, b2l_stream_t stream);
 
+/* Prefill-shaped linear (any M; meant for M > 16): y[M, N] = x[M, K] . dequant(W)^T on tcgen05 (csrc/q4_gemm.cu):
+ * 256 x 256 output tile per CTA, both operands from shared memory (producer warps dequantise the packed levels with
+ * the reference's own bf16 roundings, so the tensor core multiplies exactly get_weight()'s matrix), fp32 accumulators
+ * in tensor memory.  Same argument block as b2l_q4_linear_tc; qw_tiled from b2l_q4_tile; prologue / epilogue must be
+ * NONE / STORE; K % 64 == 0; ldx % 8 == 0.  Replaces quantization.py:187-333 (Triton tile kernel) / :413-423. */
+int b2l_q4_gemm(const b2l_q4_linear_args* args, b2l_stream_t stream);
+
 /* Batch-1 decode variant of the fused linear (M == 1): TMA-staged packed weights, PDL prefetch, persistent CTAs
  * that own 16-row blocks over the full K (no cross-CTA reduction), and an EXACT integer contraction on the legacy
  * tensor pipe: the activation row is scaled by a power of two and split into balanced base-256 digits, digit plane j

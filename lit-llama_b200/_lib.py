@@ -66,6 +66,7 @@ _SIGS = {
     "b2l_q4_tile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b2l_q4_untile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b2l_q4_linear_tc": (c_int, [C.POINTER(Q4LinearArgs), c_void_p]),
+    "b2l_q4_gemm": (c_int, [C.POINTER(Q4LinearArgs), c_void_p]),
     "b2l_q4_tiled_mma_bytes": (c_size_t, [c_int, c_int]),
     "b2l_q4_tile_mma": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b2l_q4_untile_mma": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

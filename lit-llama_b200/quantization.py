@@ -3,8 +3,9 @@
 `ColBlockQuantizedLinear` keeps the reference's constructor, attributes, buffers
 (names, shapes, dtypes, strides) and `state_dict` keys (quantization.py:340-374), so a
 `llama-gptq.4bit.pth` produced by the reference's quantize/gptq.py loads unchanged.
-`forward` runs hand-written sm_100a kernels through the C ABI of include/b2l.h; there
-is no Triton, no dense fallback and no CPU path.
+`forward` runs hand-written sm_100a kernels through the C ABI of include/b2l.h (M = 1: exact int8-digit MMA GEMV;
+2..8: f16 MMA batch kernel; 9..16: tcgen05 from tensor memory; > 16: tcgen05 256 x 256 tile GEMM); there is no
+Triton, no library GEMM, no dense fallback and no CPU path.
 """
 import ctypes as C
 import os
@@ -184,20 +185,21 @@ class ColBlockQuantizedLinear(torch.nn.Module):
                 prologue=L.PRO_NONE, norm_scale=None, eps=0.0, epilogue=L.EPI_STORE, res=None, ldres=0, split_k=0, flags=0,
                 workspace=batch_workspace(inp.device, K).data_ptr())
             L.check(L.lib().b2l_q4_gemv_batch(C.byref(a), L.stream_ptr()), "b2l_q4_gemv_batch")
-        elif self.tc_capable and aligned and M <= 64:
-            qt = self.tiled()
-            for m0 in range(0, M, 16):
-                mm = min(16, M - m0)
-                a = L.Q4LinearArgs(
-                    x=x[m0:].data_ptr(), ldx=x.stride(0), qw_tiled=qt.data_ptr(), scales=self.scales.data_ptr(),
-                    zeros=self.zeros.data_ptr(), sz_dtype=L.sz_dtype_of(self.scales), y=y[m0:].data_ptr(), ldy=N,
-                    M=mm, N=N, K=K, prologue=L.PRO_NONE, norm_scale=None, eps=0.0, epilogue=L.EPI_STORE, res=None,
-                    ldres=0, split_k=0, flags=0)
-                L.check(L.lib().b2l_q4_linear_tc(C.byref(a), L.stream_ptr()), "b2l_q4_linear_tc")
-        elif M > 64 and self.bias is None:
-            # prefill-shaped: materialise the dense weight with the reference's own rounding
-            # (get_weight) and run the plain library GEMM, as quantization.py:422-423 does
-            y = torch.nn.functional.linear(x, self.get_weight(inp.dtype))
+        elif self.tc_capable and aligned and M <= 16:
+            a = L.Q4LinearArgs(
+                x=x.data_ptr(), ldx=x.stride(0), qw_tiled=self.tiled().data_ptr(), scales=self.scales.data_ptr(),
+                zeros=self.zeros.data_ptr(), sz_dtype=L.sz_dtype_of(self.scales), y=y.data_ptr(), ldy=N,
+                M=M, N=N, K=K, prologue=L.PRO_NONE, norm_scale=None, eps=0.0, epilogue=L.EPI_STORE, res=None,
+                ldres=0, split_k=0, flags=0)
+            L.check(L.lib().b2l_q4_linear_tc(C.byref(a), L.stream_ptr()), "b2l_q4_linear_tc")
+        elif self.tc_capable and aligned and K % 64 == 0:
+            # prefill-shaped: 256 x 256 tcgen05 tiles, weights dequantised on the fly with get_weight's roundings
+            a = L.Q4LinearArgs(
+                x=x.data_ptr(), ldx=x.stride(0), qw_tiled=self.tiled().data_ptr(), scales=self.scales.data_ptr(),
+                zeros=self.zeros.data_ptr(), sz_dtype=L.sz_dtype_of(self.scales), y=y.data_ptr(), ldy=N,
+                M=M, N=N, K=K, prologue=L.PRO_NONE, norm_scale=None, eps=0.0, epilogue=L.EPI_STORE, res=None,
+                ldres=0, split_k=0, flags=0)
+            L.check(L.lib().b2l_q4_gemm(C.byref(a), L.stream_ptr()), "b2l_q4_gemm")
         else:
             self._check_layout()
             rc = L.lib().b2l_q_linear(x.data_ptr(), x.stride(0), self.quant_weight.data_ptr(), self.scales.data_ptr(),

@@ -219,6 +219,43 @@ def test_gemv_13b_65b_shapes(dev, name, N, K):
     assert relerr(y, ref_linear(xn, lv, sc, z)) < 1e-3 + 2.0 ** -9
 
 
+@pytest.mark.parametrize("M,N,K", [(17, 256, 64), (100, 384, 128), (300, 130, 256), (256, 512, 512), (257, 768, 256), (1000, 4096, 4096),
+                                   (64, 32000, 4096), (4096, 15360, 5120), (4096, 5120, 13824)])
+def test_q4_gemm_prefill_shapes(dev, M, N, K):
+    """The tcgen05 prefill GEMM (M > 16) against the reference's dense branch evaluated by torch in fp32 on the SAME
+    bf16-rounded dequantised matrix (quantization.py:392-423: get_weight rounds (level - zero) * scale to bf16, F.linear
+    accumulates): ragged M / N tiles, one k stage, the 13B widths of BASELINE configs[3] at M = 8 x 512."""
+    import ctypes as C
+
+    from gpu_util import rand_q4, relerr, tile
+    from lit_llama_b200 import _lib as L
+
+    lv, qw, sc, z = rand_q4(N, K, dev, seed=M + N + K)
+    qt = tile(L, qw, N, K)
+    x = torch.randn(M, K, device=dev).bfloat16()
+    y = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    a = L.Q4LinearArgs(x=x.data_ptr(), ldx=K, qw_tiled=qt.data_ptr(), scales=sc.data_ptr(), zeros=z.data_ptr(), sz_dtype=L.sz_dtype_of(sc),
+                       y=y.data_ptr(), ldy=N, M=M, N=N, K=K, prologue=0, norm_scale=None, eps=0.0, epilogue=0, res=None, ldres=0,
+                       split_k=0, flags=0)
+    rc = L.lib().b2l_q4_gemm(C.byref(a), L.stream_ptr())
+    assert rc == 0, L.lib().b2l_last_error()
+    torch.cuda.synchronize()
+    wb = ((lv.to(torch.bfloat16) - z.to(torch.bfloat16)) * sc.to(torch.bfloat16))     # get_weight(bf16), quantization.py:398-410
+    want = x.float() @ wb.float().t()
+    # fp32 accumulation of exact bf16 products in a different order + one bf16 rounding of the result
+    assert relerr(y, want.double()) < 2.0 ** -9, relerr(y, want.double())
+    err = (y.float() - want).abs()
+    mag = x.float().abs() @ wb.float().abs().t()
+    assert bool((err <= want.abs() * 2.0 ** -8 + mag * 2.0 ** -20 + 1e-30).all()), float((err / (want.abs() * 2.0 ** -8 + mag * 2.0 ** -20 + 1e-30)).max())
+    assert float((y == want.bfloat16()).float().mean()) > 0.98
+    if M * N <= 4096 * 5120:   # and through the module: forward() takes this kernel for M > 16
+        from lit_llama_b200.quantization import ColBlockQuantizedLinear
+        lin = ColBlockQuantizedLinear(K, N, bias=False, bits=4, tile_cols=-1).to(dev)
+        lin.quant_weight.copy_(qw); lin.scales = sc.clone(); lin.zeros = z.clone()
+        assert torch.equal(lin(x), y)
+        assert torch.equal(lin.get_weight(torch.bfloat16), wb)
+
+
 @pytest.mark.parametrize("name,N,K", [("c_attn", 12288, 4096), ("c_proj", 4096, 4096), ("c_fc12", 22016, 4096),
                                       ("mlp_proj", 4096, 11008), ("lm_head", 32000, 4096)])
 def test_tc_linear_7b_shapes(dev, name, N, K):

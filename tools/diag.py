@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "grid_flag", "hmma_rate", "imma_rate", "consumer_rate", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline", "mega_timeline"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "grid_flag", "hmma_rate", "imma_rate", "consumer_rate", "bench_gemm", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline", "mega_timeline"]
 
 
 _DLIB = None
@@ -627,6 +627,29 @@ def sec_consumer_rate():
                       f"-> {16384 / cyc:.1f} B/clk/SM = {16384 / cyc * 1.965 * 148 / 1e3:.1f} TB/s-equivalent", flush=True)
 
 
+def sec_bench_gemm():
+    """The tcgen05 prefill GEMM at the 13B widths, M = 4096 (BASELINE configs[3] prefill 8 x 512), next to torch.matmul
+    (library bf16 GEMM on a dense weight of the same shape) as the tensor-pipe yardstick."""
+    import torch
+    from lit_llama_b200 import _lib as L
+
+    dev = torch.device("cuda")
+    M = int(os.environ.get("B2L_GEMM_M", "4096"))
+    for (name, N, K) in [("c_attn", 15360, 5120), ("c_proj", 5120, 5120), ("fc1", 13824, 5120), ("mlp_proj", 5120, 13824), ("7B c_attn", 12288, 4096)]:
+        lv, qw, sc, z = rand_q4(N, K, dev, seed=3)
+        qt = tile(L, qw, N, K)
+        x = torch.randn(M, K, device=dev).bfloat16()
+        y = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        a = L.Q4LinearArgs(x=x.data_ptr(), ldx=K, qw_tiled=qt.data_ptr(), scales=sc.data_ptr(), zeros=z.data_ptr(), sz_dtype=0, y=y.data_ptr(), ldy=N,
+                           M=M, N=N, K=K, prologue=0, norm_scale=None, eps=0.0, epilogue=0, res=None, ldres=0, split_k=0, flags=0)
+        fn = lambda: L.check(L.lib().b2l_q4_gemm(C.byref(a), L.stream_ptr()), "gemm")
+        us = _time(fn, iters=10, warm=2)
+        w = torch.randn(N, K, device=dev).bfloat16()
+        us_t = _time(lambda: torch.matmul(x, w.t()), iters=10, warm=2)
+        fl = 2.0 * M * N * K
+        print(f"gemm {name} M={M} N={N} K={K}: {us:.0f} us = {fl / us / 1e6:.0f} TFLOP/s   | torch.matmul bf16: {us_t:.0f} us = {fl / us_t / 1e6:.0f} TFLOP/s", flush=True)
+
+
 def sec_trace():
     """clock64 stamps of CTA 0 of one launch: where does a CTA spend its time?"""
     import torch
@@ -792,7 +815,14 @@ def sec_bench_13b_b8():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
-        print(f"13B gptq.int4 prefill B={B} T={T}: {ms:.1f} ms  ({B * T / ms * 1e3:.0f} tokens/s; dequant + library GEMM branch)")
+        print(f"13B gptq.int4 prefill B={B} T={T}: {ms:.1f} ms  ({B * T / ms * 1e3:.0f} tokens/s; tcgen05 tile GEMM for every linear)")
+        if os.environ.get("B2L_PREFILL_PROFILE"):
+            from torch.profiler import ProfilerActivity, profile
+            model.reset_cache()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                model(idx, S, torch.arange(T, device=dev))
+                torch.cuda.synchronize()
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))
     us = _decode_us(model, B, S, dev, p0=T)
     from lit_llama_b200.quantization import BATCH_GEMV
     print(f"13B gptq.int4 decode B={B} pos~{T}: {us:.0f} us/step  {B * 1e6 / us:.0f} tokens/s  "
