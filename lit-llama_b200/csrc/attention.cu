@@ -5,6 +5,8 @@
 //
 // All positions are read on the device; the host never synchronises (the reference
 // does once per layer per token, model.py:214).
+#include <cstdlib>
+
 #include "b2l_common.cuh"
 
 namespace b2l {
@@ -503,6 +505,205 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   if (threadIdx.x == 0) tl_max(tl, 4);
 }
 
+// ----------------------------------------------------------------------------------
+// Prefill / no-cache attention for head_size 128 and T > 1 (model.py:200-230 over many query positions): a tiled
+// online-softmax kernel on the tensor cores (mma.sync.m16n8k16 bf16, fp32 accumulate).  Round 1 gave every query row
+// its own CTA that re-read all its keys from L2 (13B, 8 x 512 tokens: 153 ms of a 315 ms prefill); here a CTA owns
+// 64 query rows of one head (4 warps x 16 rows), streams 64-key K / V tiles through a double-buffered shared-memory
+// ring (cp.async, rows gathered through the cache ring), computes S = Q K^T and O += P V with ldmatrix-fed MMAs.
+// Scores are scaled and exponentiated in fp32; P enters the second MMA as bf16 hi + lo parts (2^-17 relative), so the
+// result matches an fp32 softmax(q k^T / sqrt(hs)) v to the final bf16 rounding.
+// q is read from qkv (already rotated by rope_append_kernel); the mask is "slot <= position of the query"
+// (model.py:94-96 through the tril rows selected by input_pos).
+// ----------------------------------------------------------------------------------
+constexpr int PF_Q = 64, PF_K = 64, PF_LD = 136;               // padded row: 128 + 8 elements (272 B) -> conflict-free ldmatrix
+constexpr int PF_TILE_BYTES = PF_Q * PF_LD * 2;                 // 17408
+constexpr int PF_SMEM_BYTES = 5 * PF_TILE_BYTES;                // Q + 2 x (K, V)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void pf_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// bf16 hi / lo split of two fp32 values: hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - __low2float(h), y - __high2float(h));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(128)
+    attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, KvView kv, const int64_t* __restrict__ input_pos,
+                        const int32_t* __restrict__ ring_start, __nv_bfloat16* __restrict__ y, int T, int n_head) {
+  constexpr int HS = 128;
+  extern __shared__ __align__(128) uint8_t psm[];
+  const uint32_t sq = fd_smem_u32(psm), sk0 = sq + PF_TILE_BYTES;   // K tile of buffer b at sk0 + 2 b TILE, V tile right behind it
+  const int bh = blockIdx.x, b = bh / n_head, h = bh % n_head, t0 = blockIdx.y * PF_Q;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const int C = n_head * HS;
+  const int cap = kv.S > 0 ? kv.S : T;
+  const int ring = (kv.S > 0 && ring_start) ? *ring_start : 0;
+  const __nv_bfloat16* kb = kv.k + (size_t)b * kv.b_stride + (size_t)h * kv.h_stride;
+  const __nv_bfloat16* vb = kv.v + (size_t)b * kv.b_stride + (size_t)h * kv.h_stride;
+
+  // valid slots of this thread's two query rows (g and g + 8 of the warp's 16), and of the whole CTA
+  int Lrow[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int t = min(t0 + warp * 16 + g + 8 * i, T - 1);
+    const long long p = input_pos ? input_pos[t] : (long long)t;
+    Lrow[i] = (int)(p < cap ? p : (long long)cap - 1) + 1;
+  }
+  __shared__ int s_lmax;
+  if (tid == 0) s_lmax = 0;
+  __syncthreads();
+  atomicMax(&s_lmax, max(Lrow[0], Lrow[1]));
+  // ---- Q tile (rows beyond T repeat row T - 1: never stored)
+  for (int q = tid; q < PF_Q * 16; q += 128) {
+    const int r = q >> 4, c = q & 15;
+    const int t = min(t0 + r, T - 1);
+    pf_cp16(sq + (r * PF_LD + c * 8) * 2, qkv + ((size_t)b * T + t) * 3 * C + h * HS + c * 8);
+  }
+  __syncthreads();
+  const int Lmax = s_lmax;
+  const int n_kb = (Lmax + PF_K - 1) / PF_K;
+  auto load_kv = [&](int kbi, int buf) {
+    const uint32_t dk = sk0 + buf * 2 * PF_TILE_BYTES, dv = dk + PF_TILE_BYTES;
+    for (int q = tid; q < PF_K * 16; q += 128) {
+      const int r = q >> 4, c = q & 15;
+      int j = min(kbi * PF_K + r, Lmax - 1);     // rows beyond the last valid slot repeat it (masked below)
+      if (kv.S > 0) { j += ring; if (j >= kv.S) j -= kv.S; }
+      pf_cp16(dk + (r * PF_LD + c * 8) * 2, kb + (size_t)j * kv.s_stride + c * 8);
+      pf_cp16(dv + (r * PF_LD + c * 8) * 2, vb + (size_t)j * kv.s_stride + c * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_kv(0, 0);   // group 0 also carries the Q tile
+  uint32_t qf[8][4];
+  float o[16][4];
+#pragma unroll
+  for (int n = 0; n < 16; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  const float scale = rsqrtf((float)HS);
+
+  for (int kbi = 0; kbi < n_kb; ++kbi) {
+    const int buf = kbi & 1;
+    if (kbi + 1 < n_kb) {
+      load_kv(kbi + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (kbi == 0) {   // Q fragments: 8 k-steps of 16 dims
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const int mi = lane >> 3;
+        ldsm_x4(sq + ((warp * 16 + (mi & 1) * 8 + (lane & 7)) * PF_LD + ks * 16 + (mi >> 1) * 8) * 2, qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+      }
+    }
+    const uint32_t ksm = sk0 + buf * 2 * PF_TILE_BYTES, vsm = ksm + PF_TILE_BYTES;
+    // ---- S = Q K^T for 64 keys: 8 n-tiles of 8 keys
+    float sacc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sacc[nt][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 8; ks += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(ksm + ((nt * 8 + (lane & 7)) * PF_LD + ks * 16 + (lane >> 3) * 8) * 2, b0, b1, b2, b3);
+        mma_bf16(sacc[nt], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b0, b1);
+        mma_bf16(sacc[nt], qf[ks + 1][0], qf[ks + 1][1], qf[ks + 1][2], qf[ks + 1][3], b2, b3);
+      }
+    }
+    // ---- scale, mask (slot < valid slots of the row), online softmax; lane (g, t4) holds rows g / g + 8, keys 8 nt + 2 t4 (+1)
+    float mnew[2] = {mrow[0], mrow[1]};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int key = kbi * PF_K + nt * 8 + 2 * t4 + (i & 1);
+        const float v = (key < Lrow[i >> 1]) ? sacc[nt][i] * scale : -INFINITY;
+        sacc[nt][i] = v;
+        mnew[i >> 1] = fmaxf(mnew[i >> 1], v);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 1));
+      mnew[r] = fmaxf(mnew[r], __shfl_xor_sync(0xffffffffu, mnew[r], 2));
+    }
+    float corr[2], psum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) corr[r] = (mrow[r] == -INFINITY) ? 0.f : __expf(mrow[r] - mnew[r]);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float pj = (sacc[nt][i] == -INFINITY) ? 0.f : __expf(sacc[nt][i] - mnew[i >> 1]);
+        sacc[nt][i] = pj;
+        psum[i >> 1] += pj;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      lrow[r] = lrow[r] * corr[r] + psum[r];   // per-lane partial row sums; reduced across the quad at the end
+      mrow[r] = mnew[r];
+    }
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      o[n][0] *= corr[0]; o[n][1] *= corr[0]; o[n][2] *= corr[1]; o[n][3] *= corr[1];
+    }
+    // ---- O += P V: 4 k-steps of 16 keys, 16 n-tiles of 8 dims; P as bf16 hi + lo
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t ah[4], al[4];
+      split_bf16x2(sacc[2 * kk][0], sacc[2 * kk][1], ah[0], al[0]);          // row g,     keys 16 kk + 2 t4 (+1)
+      split_bf16x2(sacc[2 * kk][2], sacc[2 * kk][3], ah[1], al[1]);          // row g + 8
+      split_bf16x2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], ah[2], al[2]);  // row g,     keys 16 kk + 8 + 2 t4 (+1)
+      split_bf16x2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ah[3], al[3]);  // row g + 8
+#pragma unroll
+      for (int dn = 0; dn < 16; dn += 2) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(vsm + ((kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PF_LD + dn * 8 + (lane >> 4) * 8) * 2, b0, b1, b2, b3);
+        mma_bf16(o[dn], ah[0], ah[1], ah[2], ah[3], b0, b1);
+        mma_bf16(o[dn], al[0], al[1], al[2], al[3], b0, b1);
+        mma_bf16(o[dn + 1], ah[0], ah[1], ah[2], ah[3], b2, b3);
+        mma_bf16(o[dn + 1], al[0], al[1], al[2], al[3], b2, b3);
+      }
+    }
+    __syncthreads();   // this buffer is refilled two iterations later
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int t = t0 + warp * 16 + g + 8 * r;
+    if (t < T) {
+      const float inv = 1.0f / lrow[r];
+      __nv_bfloat16* dst = y + ((size_t)b * T + t) * C + h * HS + 2 * t4;
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        *reinterpret_cast<__nv_bfloat162*>(dst + n * 8) = __floats2bfloat162_rn(o[n][2 * r] * inv, o[n][2 * r + 1] * inv);
+    }
+  }
+}
+
 // debug timeline slot for the next fused-attention launch (set by b2l_decode_step; nullptr = off)
 void* g_attn_timeline = nullptr;
 
@@ -514,6 +715,14 @@ static inline void split_plan(int T, int S, int* n_split, int* chunk) {
 
 static int launch_attn(const __nv_bfloat16* qkv, KvView kv, const int64_t* input_pos, const int32_t* ring_start,
                        float* work, __nv_bfloat16* y, int B, int T, int n_head, int hs, int cap, cudaStream_t st) {
+  static const int env_pf = [] { const char* e = getenv("B2L_ATTN_PREFILL"); return e ? atoi(e) : 1; }();
+  if (hs == 128 && T > 1 && env_pf) {   // tiled tensor-core kernel (B2L_ATTN_PREFILL=0: the per-query path below)
+    static DynSmemCache smem_cache;
+    if (int rc = ensure_dyn_smem(attn_prefill_kernel, PF_SMEM_BYTES, smem_cache)) return rc;
+    attn_prefill_kernel<<<dim3(B * n_head, (T + PF_Q - 1) / PF_Q), 128, PF_SMEM_BYTES, st>>>(qkv, kv, input_pos, ring_start, y, T, n_head);
+    B2L_LAUNCH_CHECK("attn_prefill_kernel");
+    return 0;
+  }
   int n_split, chunk;
   split_plan(T, cap, &n_split, &chunk);
   dim3 grid(B * n_head, T, n_split), block(ATT_WARPS * 32);

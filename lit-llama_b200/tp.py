@@ -21,6 +21,7 @@ the K slice, so each rank's kernel uses its LOCAL sum(x) and the partial results
 The per-rank partial products are rounded to bf16 before the reduction (the kernels' output
 dtype), so a TP result can differ from the single-GPU one by one bf16 ulp per reduction.
 """
+import ctypes as C
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -113,6 +114,107 @@ class _TPBlock(nn.Module):
         self.mlp = _TPMLP(C, nh_l)
 
 
+class _TPDecodeState:
+    """Batch-1 decode step of one rank as a fixed launch sequence over static buffers (captured once into a CUDA graph,
+    NCCL all-reduces included): the single-GPU path's fused kernels on the local shards --
+      [rms_1 + c_attn(local heads)] -> fused attention (local heads) -> [c_proj (K = local heads) (+ residual on rank 0)]
+      -> all-reduce -> [rms_2 + c_fc1|c_fc2 (local columns) + SwiGLU] -> [mlp.c_proj (K = local columns) (+ residual on
+      rank 0)] -> all-reduce; finally [ln_f + lm_head (local vocabulary rows)] -> all-gather.
+    The residual enters the sum exactly once (rank 0's epilogue), so all-reduce(sum) leaves x + sum_r partial_r on every
+    rank (model.py:166-167).  Two all-reduces per Block."""
+
+    def __init__(self, m: "TPLLaMA", S: int, dev: torch.device, idx_dtype: torch.dtype) -> None:
+        cfg, lib = m.config, L.lib()
+        Cd, hs, nh_l, world = cfg.n_embd, m.hs, m.nh_l, m.world
+        C_l = nh_l * hs
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        self.idx = torch.zeros(1, dtype=idx_dtype, device=dev)
+        self.pos = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.x = torch.empty((1, Cd), **bf)
+        self.qkv = torch.empty((1, 3 * C_l), **bf)
+        self.att = torch.empty((1, C_l), **bf)
+        hid_l = m.transformer.h[0].mlp.c_fc1.out_features
+        self.hid = torch.empty((1, hid_l), **bf)
+        V_l = m.lm_head.out_features
+        self.logits_l = torch.empty((1, V_l), **bf)
+        self.logits = torch.empty((world, V_l), **bf)
+        self.work = torch.zeros(lib.b2l_attn_workspace_bytes(1, nh_l, hs, 1, S) // 4 + 1, device=dev, dtype=torch.float32)
+        self.keep: List[torch.Tensor] = []
+        szd = L.sz_dtype_of(m.lm_head.scales)
+        eps = float(m.transformer.ln_f.eps)
+
+        def bf16(p: torch.Tensor) -> torch.Tensor:
+            t = p.detach()
+            if t.dtype != torch.bfloat16:
+                t = t.to(torch.bfloat16)
+            self.keep.append(t)
+            return t
+
+        def gemv(tiled, scales, zeros, N, K, x, y, pro, ns, epi, res):
+            self.keep += [tiled, scales, zeros]
+            return L.Q4LinearArgs(x=x.data_ptr(), ldx=K, qw_tiled=tiled.data_ptr(), scales=scales.data_ptr(), zeros=zeros.data_ptr(),
+                                  sz_dtype=szd, y=y.data_ptr(), ldy=N, M=1, N=N, K=K, prologue=pro,
+                                  norm_scale=None if ns is None else ns.data_ptr(), eps=eps, epilogue=epi,
+                                  res=None if res is None else res.data_ptr(), ldres=N, split_k=0, flags=L.F_PDL)
+
+        def lin(l: ColBlockQuantizedLinear, x, y, pro=L.PRO_NONE, ns=None, epi=L.EPI_STORE, res=None):
+            return gemv(l.tiled_i8(), l.scales, l.zeros, l.out_features, l.in_features, x, y, pro, ns, epi, res)
+
+        def fc12(mlp):   # c_fc1 | c_fc2 interleaved 8 rows / 8 rows per 16-row block, so SwiGLU runs in the epilogue
+            nh, K = mlp.c_fc1.out_features, mlp.c_fc1.in_features
+
+            def inter(a, b):
+                return torch.stack((a.reshape(nh // 8, 8, *a.shape[1:]), b.reshape(nh // 8, 8, *b.shape[1:])), dim=1).reshape(2 * nh, *a.shape[1:])
+
+            qw = inter(mlp.c_fc1.quant_weight, mlp.c_fc2.quant_weight).t().contiguous().t()
+            sc, z = inter(mlp.c_fc1.scales, mlp.c_fc2.scales).contiguous(), inter(mlp.c_fc1.zeros, mlp.c_fc2.zeros).contiguous()
+            t = torch.empty(lib.b2l_q4_tiled_i8_bytes(2 * nh, K), dtype=torch.uint8, device=qw.device)
+            L.check(lib.b2l_q4_tile_i8(qw.data_ptr(), t.data_ptr(), 2 * nh, K, L.stream_ptr()), "b2l_q4_tile_i8")
+            return t, sc, z, 2 * nh, K
+
+        rank0 = m.rank == 0
+        self.ops = []   # ("gemv", args) | ("attn", layer index) | ("allreduce", tensor) | ("allgather",)
+        for i, blk in enumerate(m.transformer.h):
+            self.ops.append(("gemv", lin(blk.attn.c_attn, self.x, self.qkv, L.PRO_RMSNORM, bf16(blk.rms_1.scale))))
+            self.ops.append(("attn", i))
+            self.ops.append(("gemv", lin(blk.attn.c_proj, self.att, self.x, epi=L.EPI_RESIDUAL if rank0 else L.EPI_STORE, res=self.x if rank0 else None)))
+            self.ops.append(("allreduce", self.x))
+            t, sc, z, N2, K2 = fc12(blk.mlp)
+            self.ops.append(("gemv", gemv(t, sc, z, N2, K2, self.x, self.hid, L.PRO_RMSNORM, bf16(blk.rms_2.scale), L.EPI_SWIGLU, None)))
+            self.ops.append(("gemv", lin(blk.mlp.c_proj, self.hid, self.x, epi=L.EPI_RESIDUAL if rank0 else L.EPI_STORE, res=self.x if rank0 else None)))
+            self.ops.append(("allreduce", self.x))
+        self.ops.append(("gemv", lin(m.lm_head, self.x, self.logits_l, L.PRO_RMSNORM, bf16(m.transformer.ln_f.scale))))
+        self.ops.append(("allgather",))
+        self.m, self.S = m, S
+        self.wte = bf16(m.transformer.wte.weight)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.calls = 0
+        self.n_kernels = sum(1 for o in self.ops if o[0] in ("gemv", "attn")) + 2
+
+    def enqueue(self) -> None:
+        m, lib, sp = self.m, L.lib(), L.stream_ptr()
+        cfg = m.config
+        L.check(lib.b2l_ring_advance(self.pos.data_ptr(), 1, m._ring.data_ptr(), self.S, sp), "b2l_ring_advance")
+        L.check(lib.b2l_embedding(self.idx.data_ptr(), 1 if self.idx.dtype == torch.int64 else 0, self.wte.data_ptr(), self.x.data_ptr(), 1,
+                                  cfg.n_embd, self.wte.shape[0], sp), "b2l_embedding")
+        for op in self.ops:
+            if op[0] == "gemv":
+                L.check(lib.b2l_q4_gemv(C.byref(op[1]), sp), "b2l_q4_gemv")
+            elif op[0] == "attn":
+                k_c, v_c = m.kv_caches[op[1]]
+                L.check(lib.b2l_attention(self.qkv.data_ptr(), k_c.data_ptr(), v_c.data_ptr(), m.rope_cache.data_ptr(), self.pos.data_ptr(),
+                                          m._ring.data_ptr(), self.att.data_ptr(), self.work.data_ptr(), 1, 1, m.nh_l, m.hs, self.S,
+                                          cfg.block_size, L.F_PDL, sp), "b2l_attention")
+            elif op[0] == "allreduce":
+                if m.world > 1:
+                    dist.all_reduce(op[1], op=dist.ReduceOp.SUM, group=m.group)
+            else:
+                if m.world > 1:
+                    dist.all_gather_into_tensor(self.logits, self.logits_l, group=m.group)
+                else:
+                    self.logits.copy_(self.logits_l)
+
+
 class TPLLaMA(nn.Module):
     """LLaMA.forward (model.py:76-122) with every quantized linear sharded over `group`.
     State-dict keys equal the reference's, so `load_state_dict(shard_state_dict(full, rank, world, n_head))` works."""
@@ -135,9 +237,15 @@ class TPLLaMA(nn.Module):
         self.kv_caches: List[Tuple[torch.Tensor, torch.Tensor]] = []
         self._ring: Optional[torch.Tensor] = None
         self._work: Optional[torch.Tensor] = None
+        self._decode: Optional[_TPDecodeState] = None
+        #: replay the batch-1 decode step as a CUDA graph (NCCL collectives included) after this many eager steps (0 = never)
+        self.graph_after = 2
+        #: fused per-rank decode step (batch 1, head_size 128, K % 64 == 0); False: module by module
+        self.fast_decode = True
 
     def reset_cache(self) -> None:
         self.kv_caches.clear()
+        self._decode = None
         if self._ring is not None:
             self._ring.zero_()
 
@@ -171,6 +279,27 @@ class TPLLaMA(nn.Module):
         wte = self.transformer.wte.weight
         if wte.dtype != torch.bfloat16:
             raise RuntimeError("TPLLaMA: the model must be bf16")
+        # ---- batch-1 decode: the fused per-rank step, graph-replayed
+        C_l, hid_l = nh_l * hs, self.transformer.h[0].mlp.c_fc1.out_features
+        if (self.fast_decode and B == 1 and T == 1 and hs == 128 and C % 64 == 0 and C_l % 64 == 0 and hid_l % 64 == 0 and hid_l % 8 == 0
+                and self.lm_head.out_features % 16 == 0 and idx.dtype in (torch.int32, torch.int64) and self.lm_head.gemv_capable):
+            st = self._decode
+            if st is None or st.S != S or st.idx.dtype != idx.dtype:
+                st = self._decode = _TPDecodeState(self, S, dev, idx.dtype)
+            st.idx.copy_(idx.reshape(-1))
+            st.pos.copy_(pos[-1:])
+            if st.graph is not None:
+                st.graph.replay()
+            elif self.graph_after and st.calls >= self.graph_after:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st.enqueue()
+                st.graph = g
+                g.replay()
+            else:
+                st.enqueue()
+            st.calls += 1
+            return st.logits.reshape(1, 1, -1).clone()
         idx_c = idx.contiguous() if idx.dtype in (torch.int32, torch.int64) else idx.to(torch.int64).contiguous()
         x = torch.empty((B, T, C), device=dev, dtype=torch.bfloat16)
         L.check(lib.b2l_embedding(idx_c.data_ptr(), 1 if idx_c.dtype == torch.int64 else 0, wte.data_ptr(), x.data_ptr(), B * T, C,

@@ -264,6 +264,62 @@ def test_fused_attention_vs_oracle_hs128(dev, B):
         assert torch.equal(k1[:, :, phys].cpu(), k[:, :, 0]) and torch.equal(v1[:, :, phys].cpu(), v[:, :, 0]), (pos, ring0)
 
 
+@pytest.mark.parametrize("ring0", [0, 37])
+def test_prefill_attention_hs128_vs_oracle(dev, ring0):
+    """T > 1 at head_size 128 (the tiled tensor-core prefill kernel): a 150-token chunk appended at positions 40..189
+    of a partly filled (and possibly rotated) cache, and a 130-token no-cache forward, against the oracle's
+    rope_apply + index_copy + masked fp32 sdpa (model.py:200-230)."""
+    from lit_llama_b200 import _lib as L
+
+    B, nh, hs, S, blk = 2, 3, 128, 256, 512
+    C = nh * hs
+    lib = L.lib()
+    g = torch.Generator(device=dev).manual_seed(5 + ring0)
+    rope = O.rope_table(blk, hs)
+    rope_d = rope.to(dev)
+    kc = (torch.randn(B, nh, S, hs, device=dev, generator=g) * 0.5).bfloat16()
+    vc = (torch.randn(B, nh, S, hs, device=dev, generator=g) * 0.5).bfloat16()
+    p0, T = 40, 150
+    qkv = torch.randn(B, T, 3 * C, device=dev, generator=g).bfloat16()
+    k1, v1, q1 = kc.clone(), vc.clone(), qkv.clone()
+    ring = torch.tensor([ring0], dtype=torch.int32, device=dev)
+    pos = torch.arange(p0, p0 + T, dtype=torch.int64, device=dev)
+    work = torch.zeros(lib.b2l_attn_workspace_bytes(B, nh, hs, T, S) // 4 + 1, device=dev, dtype=torch.float32)
+    y = torch.empty(B, T, C, device=dev, dtype=torch.bfloat16)
+    rc = lib.b2l_attention(q1.data_ptr(), k1.data_ptr(), v1.data_ptr(), rope_d.data_ptr(), pos.data_ptr(), ring.data_ptr(), y.data_ptr(),
+                           work.data_ptr(), B, T, nh, hs, S, blk, 0, L.stream_ptr())
+    assert rc == 0, lib.b2l_last_error()
+    torch.cuda.synchronize()
+    kl, vl = torch.roll(kc.cpu(), -ring0, dims=2), torch.roll(vc.cpu(), -ring0, dims=2)
+    q, k, v = qkv.cpu().split(C, dim=2)
+    rows = rope[p0 : p0 + T]
+    q = O.rope_apply(q.view(B, T, nh, hs), rows).transpose(1, 2)
+    k = O.rope_apply(k.view(B, T, nh, hs), rows).transpose(1, 2)
+    v = v.view(B, T, nh, hs).transpose(1, 2)
+    kl = kl.index_copy(2, pos.cpu(), k)
+    vl = vl.index_copy(2, pos.cpu(), v)
+    mask = (torch.arange(S).view(1, S) <= pos.cpu().view(T, 1)).view(1, 1, T, S)
+    want = O.sdpa(q, kl, vl, mask).transpose(1, 2).reshape(B, T, C)
+    torch.testing.assert_close(y.float().cpu(), want.float(), rtol=2 ** -7, atol=2e-3)
+    assert (y.float().cpu() - want.float()).norm() / want.float().norm() < 4e-3
+    # ---- no cache (input_pos is None, model.py:104-106)
+    T2 = 130
+    qkv2 = torch.randn(B, T2, 3 * C, device=dev, generator=g).bfloat16()
+    q2 = qkv2.clone()
+    y2 = torch.empty(B, T2, C, device=dev, dtype=torch.bfloat16)
+    work2 = torch.zeros(lib.b2l_attn_workspace_bytes(B, nh, hs, T2, T2) // 4 + 1, device=dev, dtype=torch.float32)
+    rc = lib.b2l_attention_nocache(q2.data_ptr(), rope_d.data_ptr(), y2.data_ptr(), work2.data_ptr(), B, T2, nh, hs, blk, L.stream_ptr())
+    assert rc == 0, lib.b2l_last_error()
+    torch.cuda.synchronize()
+    q, k, v = qkv2.cpu().split(C, dim=2)
+    q = O.rope_apply(q.view(B, T2, nh, hs), rope[:T2]).transpose(1, 2)
+    k = O.rope_apply(k.view(B, T2, nh, hs), rope[:T2]).transpose(1, 2)
+    v = v.view(B, T2, nh, hs).transpose(1, 2)
+    mask = torch.tril(torch.ones(T2, T2, dtype=torch.bool)).view(1, 1, T2, T2)
+    want2 = O.sdpa(q, k, v, mask).transpose(1, 2).reshape(B, T2, C)
+    torch.testing.assert_close(y2.float().cpu(), want2.float(), rtol=2 ** -7, atol=2e-3)
+
+
 def test_batched_decode_rows_are_independent(dev):
     from gpu_util import build_tiny
 
