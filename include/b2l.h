@@ -84,6 +84,7 @@ enum {
                            y = bf16(bf16(silu(bf16(a))) * bf16(b))   model.py:252     */
 };
 
+#define B2L_PF_SEGMENTS 4
 typedef struct b2l_q4_linear_args {
   const void* x;        /* bf16 [M, K], leading dim ldx                               */
   int ldx;
@@ -107,6 +108,13 @@ typedef struct b2l_q4_linear_args {
   void* workspace;      /* b2l_q4_gemv_batch only: b2l_q4_gemv_batch_workspace_bytes(K) bytes of device
                            scratch, 16-byte aligned (activation fragments; may be shared by all
                            launches of one stream)                                       */
+  const void* pf_ptr[B2L_PF_SEGMENTS];          /* b2l_q4_gemv only, L2 prefetch hint: byte ranges (16-byte aligned,
+                           multiples of 16; NULL / 0 = unused) that LATER launches will stream - typically the
+                           weights of the next linears.  The CTAs ask the L2 for them as soon as their own
+                           weight ring is full, so HBM keeps streaming while this launch waits for its
+                           activations, reduces and writes its result (the reference has no counterpart:
+                           quantization.py:284-333 launches one Triton kernel per linear)          */
+  unsigned long long pf_bytes[B2L_PF_SEGMENTS];
 } b2l_q4_linear_args;
 
 enum {

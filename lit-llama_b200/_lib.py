@@ -26,6 +26,7 @@ class Q4LinearArgs(C.Structure):
         ("prologue", c_int), ("norm_scale", c_void_p), ("eps", c_float),
         ("epilogue", c_int), ("res", c_void_p), ("ldres", c_int),
         ("split_k", c_int), ("flags", c_int), ("trace", c_void_p), ("workspace", c_void_p),
+        ("pf_ptr", c_void_p * 4), ("pf_bytes", C.c_ulonglong * 4),
     ]
 
 

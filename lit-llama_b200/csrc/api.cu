@@ -1,5 +1,9 @@
 // Error state, device facts and the whole-token entry point of libb200llama.
+#include <algorithm>
+#include <cstdlib>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "b2l_common.cuh"
 
@@ -62,10 +66,63 @@ extern "C" int b2l_device_info(int* sm, int* cc_major, int* cc_minor) {
 // Per Block: [rms_1 + c_attn] -> rope/append/attention -> [c_proj + residual]
 //            -> [rms_2 + c_fc1|c_fc2 + silu*mul] -> [mlp.c_proj + residual]
 // ---------------------------------------------------------------------------------
+// ---- L2 prefetch windows of the batch-1 step (b2l_q4_linear_args::pf_ptr).
+// The packed weights of a token are read in a fixed order: per Block c_attn, c_proj, fc1|fc2, mlp.c_proj, then lm_head,
+// then the next token's Block 0 again.  Seen as one byte stream, launch j (bytes [S_j, E_j)) asks the L2 for
+// [max(S_j + D, E_j), E_j + D): after every launch everything up to D bytes beyond its own end has been requested, so
+// HBM always has a backlog to work on while a launch waits for its activations (prologue), reduces and stores
+// (epilogue) or the attention kernel runs.  D = B2L_PF_MB (MB, read once; 0 switches the hint off).
+struct PfWindow { const void* ptr[B2L_PF_SEGMENTS]; unsigned long long bytes[B2L_PF_SEGMENTS]; };
+
+static size_t prefetch_distance() {
+  static const long mb = [] { const char* e = getenv("B2L_PF_MB"); return e ? atol(e) : 0L; }();
+  return mb > 0 ? (size_t)mb << 20 : 0;
+}
+
+static std::vector<PfWindow> prefetch_windows(const b2l_decode_args* d) {
+  std::vector<std::pair<const uint8_t*, size_t>> ops;
+  auto add = [&](const b2l_q4_weight& w) { ops.push_back({(const uint8_t*)w.qw_mma, b2l_q4_tiled_i8_bytes(w.N, w.K)}); };
+  for (int l = 0; l < d->n_layer; ++l) {
+    add(d->layers[l].c_attn); add(d->layers[l].c_proj); add(d->layers[l].c_fc12); add(d->layers[l].mlp_proj);
+  }
+  add(d->lm_head);
+  const size_t n = ops.size(), D = prefetch_distance();
+  std::vector<PfWindow> out(n, PfWindow{});
+  if (D == 0) return out;
+  std::vector<size_t> start(n + 1, 0);
+  for (size_t j = 0; j < n; ++j) start[j + 1] = start[j] + ops[j].second;
+  const size_t total = start[n];
+  for (size_t j = 0; j < n; ++j) {
+    size_t lo = std::max(start[j] + D, start[j + 1]), hi = start[j + 1] + D;   // may run past `total`: wraps to the next token
+    int sg = 0;
+    size_t k = j + 1;      // first op at or after `lo` (positions counted from this token's start; op k lives at k % n)
+    size_t base = start[j + 1];
+    while (lo < hi && sg < B2L_PF_SEGMENTS && k < j + 1 + n) {
+      const auto& op = ops[k % n];
+      const size_t op_lo = base, op_hi = base + op.second;
+      if (lo < op_hi) {
+        const size_t a = (lo - op_lo) & ~(size_t)127, b = std::min(hi, op_hi) - op_lo;
+        if (b > a && op.first != nullptr) {
+          out[j].ptr[sg] = op.first + a;
+          out[j].bytes[sg] = (b - a + 15) & ~(size_t)15;
+          ++sg;
+        }
+        lo = std::min(hi, op_hi);
+      }
+      base = op_hi;
+      ++k;
+    }
+    (void)total;
+  }
+  return out;
+}
+
 static int q4_call(const b2l_q4_weight& w, const void* x, int ldx, void* y, int ldy, int M, int sz_dtype, int prologue,
                    const void* norm_scale, float eps, int epilogue, const void* res, int ldres, int flags,
-                   b2l_stream_t stream, void* trace = nullptr, void* batch_work = nullptr) {
+                   b2l_stream_t stream, void* trace = nullptr, void* batch_work = nullptr, const PfWindow* pf = nullptr) {
   b2l_q4_linear_args a{};
+  if (pf != nullptr)
+    for (int i = 0; i < B2L_PF_SEGMENTS; ++i) { a.pf_ptr[i] = pf->ptr[i]; a.pf_bytes[i] = pf->bytes[i]; }
   a.x = x; a.ldx = ldx;
   const bool gemv = (M == 1 && w.qw_mma != nullptr);
   const bool batch = (!gemv && M <= 8 && w.qw_mma != nullptr && batch_work != nullptr);
@@ -114,12 +171,17 @@ extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {
   char* tlb = (char*)d->timeline;
   int li = 0;
   auto tl = [&]() -> void* { void* r = tlb ? (void*)(tlb + 512 * li) : nullptr; ++li; return r; };
+  // batch 1 on the int8-MMA kernel: every linear carries the L2 prefetch window of the weights that follow it
+  std::vector<PfWindow> pfw;
+  if (B == 1 && d->lm_head.qw_mma != nullptr) pfw = prefetch_windows(d);
+  int oi = 0;
+  auto pf = [&]() -> const PfWindow* { const PfWindow* r = pfw.empty() ? nullptr : &pfw[oi]; ++oi; return r; };
   if ((rc = b2l_ring_advance(d->input_pos, 1, d->ring_start, d->S, stream))) return rc;
   if ((rc = b2l_embedding(d->idx, d->idx_is_i64, d->wte, d->x, B, C, d->vocab, stream))) return rc;
   for (int l = 0; l < d->n_layer; ++l) {
     const b2l_layer& L = d->layers[l];
     if ((rc = q4_call(L.c_attn, d->x, C, d->qkv, 3 * C, B, d->sz_dtype, B2L_PRO_RMSNORM, L.rms_1, d->eps, B2L_EPI_STORE,
-                      nullptr, 0, fl, stream, tl(), d->batch_work)))
+                      nullptr, 0, fl, stream, tl(), d->batch_work, pf())))
       return rc;
     g_attn_timeline = tl();
     if ((rc = b2l_attention(d->qkv, L.k_cache, L.v_cache, d->rope, d->input_pos, d->ring_start, d->att, d->attn_work, B,
@@ -129,15 +191,15 @@ extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {
     }
     g_attn_timeline = nullptr;
     if ((rc = q4_call(L.c_proj, d->att, C, d->x, C, B, d->sz_dtype, B2L_PRO_NONE, nullptr, 0.f, B2L_EPI_RESIDUAL, d->x, C,
-                      fl, stream, tl(), d->batch_work)))
+                      fl, stream, tl(), d->batch_work, pf())))
       return rc;
     if ((rc = q4_call(L.c_fc12, d->x, C, d->hid, d->n_hidden, B, d->sz_dtype, B2L_PRO_RMSNORM, L.rms_2, d->eps,
-                      B2L_EPI_SWIGLU, nullptr, 0, fl, stream, tl(), d->batch_work)))
+                      B2L_EPI_SWIGLU, nullptr, 0, fl, stream, tl(), d->batch_work, pf())))
       return rc;
     if ((rc = q4_call(L.mlp_proj, d->hid, d->n_hidden, d->x, C, B, d->sz_dtype, B2L_PRO_NONE, nullptr, 0.f,
-                      B2L_EPI_RESIDUAL, d->x, C, fl, stream, tl(), d->batch_work)))
+                      B2L_EPI_RESIDUAL, d->x, C, fl, stream, tl(), d->batch_work, pf())))
       return rc;
   }
   return q4_call(d->lm_head, d->x, C, d->logits, d->vocab, B, d->sz_dtype, B2L_PRO_RMSNORM, d->ln_f, d->eps,
-                 B2L_EPI_STORE, nullptr, 0, fl, stream, tl(), d->batch_work);
+                 B2L_EPI_STORE, nullptr, 0, fl, stream, tl(), d->batch_work, pf());
 }

@@ -8,8 +8,9 @@
 //
 // The contraction y[o] = scale[o] * sum_k (level[o,k] - zero[o]) * x[k] is evaluated in EXACT integer arithmetic:
 //   * the activation row (after the RMSNorm prologue, i.e. the bf16 values the reference feeds its linear) is
-//     scaled by a power of two 2^sh chosen from max|x| and rounded to X[k] (|X| < 2^30 with four digits, 2^22 with
-//     three), then split into balanced base-256 digits X = sum_j d_j 256^j, d_j in [-128, 127];
+//     scaled by a power of two 2^sh chosen from max|x| and rounded to X[k] (|X| < 2^22: 14 bits of dynamic range
+//     below the largest element before an 8-bit significand loses a bit, and a rounding unit of 2^-22 max|x| from
+//     there on), then split into three balanced base-256 digits X = sum_j d_j 256^j, d_j in [-128, 127];
 //   * mma.sync.m16n8k32 (u8 x s8 -> s32, SASS IMMA.16832.U8.S8) has 8 result columns and a single activation row
 //     needs one: digit plane j is column j, so all digits cost ONE MMA per 16 x 32 weight tile;
 //   * a packed byte holds two levels.  It is fed to the tensor core UNMASKED as the operand of row g (value
@@ -55,7 +56,14 @@ struct Params {
   int nst;               // ring stages
   unsigned long long* tl;  // debug timeline (nullptr = off)
   int nocompute;           // debug: consumers release every stage untouched (pure TMA streaming rate)
+  // L2 prefetch hint (b2l_q4_linear_args::pf_ptr): byte ranges later launches stream; CTA c asks for the c-th slice
+  const uint8_t* pf_ptr[B2L_PF_SEGMENTS];
+  uint32_t pf_bytes[B2L_PF_SEGMENTS];
+  int pf_mode;             // 0 off, 1 bulk prefetch by the producer lane, 2 / 4 per-line prefetch (128 B / 32 B apart)
+  int evict_first;         // demand loads carry an L2 evict_first policy (a weight byte is read once per token)
 };
+
+constexpr uint32_t PF_CHUNK = 16384;   // bytes per bulk L2 prefetch instruction
 
 // digit-plane stride in bytes: one byte per k, padded so that planes n and n + 1 fall into different bank halves
 __host__ __device__ inline uint32_t plane_stride(int K) { return (uint32_t)K + ((K % 128 == 0) ? 64u : 0u); }
@@ -71,10 +79,30 @@ __host__ __device__ inline SmemLayout smem_layout(int nst, int K, int ndig) {
   L.xf = o;      o += (uint32_t)ndig * plane_stride(K);   // digit planes: [digit][k block][t (4)][16 B]
   L.zero = o;    o += 16;                                 // the B operand of the unused MMA columns
   L.scratch = o; o += 2 * NCW * MAX_HALVES * RB * 16;     // [buf][warp][half][row][digit (4)] int32 partials
-  L.red = o;     o += 192;                                // reductions: float[8] sumsq, float[8] max, int64[8] sum X, int sh
+  L.red = o;     o += 192;                                // reductions: float[8] sumsq, float[8] max, int64[8] sum X, int sh, float[8] max|g|
   L.bars = o;    o += 2 * MAX_STAGES * 8;
   L.total = (o + 127u) & ~127u;
   return L;
+}
+
+// ---- L2 prefetch of weights a later launch reads (no shared memory, no completion: fire and forget)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_line(const void* src) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+}
+// this CTA's slice [lo, hi) of a segment of `bytes` bytes, cut at 128-byte lines
+__device__ __forceinline__ void pf_slice(uint32_t bytes, uint32_t& lo, uint32_t& hi) {
+  const uint32_t lines = (bytes + 127u) >> 7;
+  lo = (uint32_t)(((unsigned long long)blockIdx.x * lines) / gridDim.x) << 7;
+  hi = min((uint32_t)(((unsigned long long)(blockIdx.x + 1) * lines) / gridDim.x) << 7, bytes);
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(mbar), "l"(policy)
+      : "memory");
 }
 
 // X (|X| < 2^30) -> word whose bytes are its balanced base-256 digits (byte 3 = signed top digit)
@@ -100,7 +128,7 @@ __device__ __forceinline__ void single_imma(int (&a)[2][4], const uint8_t* tile,
 
 // MAXC = activation chunks (2048 elements each) a thread block caches in registers during the prologue:
 // 6 covers K <= 12288 (every 7B/13B/30B layer), 12 covers K <= 24576 (65B mlp.c_proj, K = 22016).
-// NDIG = base-256 digits of the scaled activations: 4 (|X| < 2^30) or 3 (|X| < 2^22; wide K, smaller planes).
+// NDIG = base-256 digits of the scaled activations: 3 (|X| < 2^22).
 template <int MAXC, int NDIG>
 __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -136,6 +164,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
       int slot = 0;
       uint32_t phase = 1;  // fresh barriers: waiting on parity 1 passes immediately
       int it = 0;
+      uint64_t policy = 0;
+      if (p.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       for (int u = 0; u < n_units; ++u) {
         const int rb = rb_lo + 2 * u;
         const int halves = min(2, rb_hi - rb);
@@ -146,11 +176,28 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
           const uint32_t bytes = (uint32_t)nkb * KB_BYTES;
           mbar_wait(bar_empty + slot * 8, phase);
           mbar_expect_tx(bar_full + slot * 8, bytes * halves);
-          for (int h = 0; h < halves; ++h)
-            tma_bulk_g2s(sbase + L.ring + slot * STAGE_BYTES + h * HALF_STAGE_BYTES,
-                         src + ((size_t)h * n_kb + kb0) * KB_BYTES, bytes, bar_full + slot * 8);
+          for (int h = 0; h < halves; ++h) {
+            const uint32_t dst = sbase + L.ring + slot * STAGE_BYTES + h * HALF_STAGE_BYTES;
+            const uint8_t* from = src + ((size_t)h * n_kb + kb0) * KB_BYTES;
+            if (p.evict_first) tma_bulk_g2s_hint(dst, from, bytes, bar_full + slot * 8, policy);
+            else tma_bulk_g2s(dst, from, bytes, bar_full + slot * 8);
+          }
           if (++slot == p.nst) { slot = 0; phase ^= 1; }
-          if (it + 1 == min(total_stages, p.nst)) pdl_launch_dependents();  // ring full: next kernel may prefetch
+          if (it + 1 == min(total_stages, p.nst)) {
+            pdl_launch_dependents();  // ring full: next kernel may prefetch
+            if (p.pf_mode == 1) {
+              // the ring is full and this lane would now wait for a free slot: queue the L2 prefetch of this CTA's
+              // slice of the weights the following launches read (HBM keeps streaming through the activation waits)
+#pragma unroll
+              for (int sgi = 0; sgi < B2L_PF_SEGMENTS; ++sgi) {
+                if (p.pf_bytes[sgi] == 0) continue;
+                uint32_t lo, hi;
+                pf_slice(p.pf_bytes[sgi], lo, hi);
+#pragma unroll 1
+                for (uint32_t o = lo; o < hi; o += PF_CHUNK) l2_prefetch_bulk(p.pf_ptr[sgi] + o, min(PF_CHUNK, hi - o));
+              }
+            }
+          }
         }
       }
       if (total_stages == 0) pdl_launch_dependents();
@@ -160,18 +207,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
     float* red = reinterpret_cast<float*>(smem + L.red);   // [0..7] sum of squares, [8..15] max, then int64[8] sum X, int sh
     long long* red_sx = reinterpret_cast<long long*>(smem + L.red + 64);
     int* red_sh = reinterpret_cast<int*>(smem + L.red + 128);
-    // ---- activations: [RMSNorm], power-of-two scaling, balanced digits in B-fragment order, exact sum(X)
+    // ---- activations: [RMSNorm], power-of-two scaling, balanced digits in B-fragment order, exact sum(X).
+    // Every CTA converts the whole row (K values, 296 times per launch), and the launch cannot start its main loop
+    // before this is done: the conversion is written for instruction count.  Per pair of elements: packed bf16
+    // max / multiplies, ONE fma that both scales and rounds to an integer (x * 2^sh + 1.5 * 2^23: the integer sits
+    // in the mantissa, |X| < 2^22 -- no F2I, which runs at a quarter of the fp32 rate), the balanced digits straight
+    // from those bits with one add and one xor.
     {
       const bool norm = (p.prologue == B2L_PRO_RMSNORM);
       constexpr int NT = NCW * 32;   // 256 threads, 8 elements each per pass
+      constexpr uint32_t MAGIC_BITS = 0x4B400000u;   // 1.5 * 2^23
       uint4 xv[MAXC], gv[MAXC];
-      // the RMSNorm scale is a weight: fetch it BEFORE waiting for the producing kernel (it comes from HBM,
-      // behind the queued weight prefetch; after the wait it would sit on the critical path)
+      // the RMSNorm scale is a weight: fetch it (and reduce its max) BEFORE waiting for the producing kernel
+      __nv_bfloat162 gmax2 = __float2bfloat162_rn(0.f);
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         const int k = (c * NT + tid) * 8;
         gv[c] = make_uint4(0, 0, 0, 0);
         if (norm && k < p.K) gv[c] = *reinterpret_cast<const uint4*>(p.norm_scale + k);
+      }
+      if (norm) {
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          const uint32_t g[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gmax2 = __hmax2(gmax2, __habs2(*reinterpret_cast<const __nv_bfloat162*>(&g[q])));
+        }
       }
       pdl_wait();
       if (tid == 0) tl_max(p.tl, 1);
@@ -183,49 +244,49 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
         if (k < p.K) xv[c] = ld_coherent_u4(p.x + k);
       }
       const int nchunk = (p.K + NT * 8 - 1) / (NT * 8);  // warp-uniform: chunks that hold data
-      // pass 1: sum of bf16-rounded squares (RMSNorm, model.py:274) and max |x * scale| (bounds the normalised values)
-      // bf16x2 arithmetic: one HMUL2 is the exactly-rounded bf16 product the reference computes
-      float ss = 0.f, mx = 0.f;
+      // pass 1: sum of bf16-rounded squares (RMSNorm, model.py:274: one HMUL2 is the exactly-rounded bf16 product the
+      // reference computes) and max |x| (with max |scale| it bounds the normalised values)
+      float ss = 0.f;
+      __nv_bfloat162 amax2 = __float2bfloat162_rn(0.f);
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         if (c < nchunk) {
           const uint32_t w[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
-          const uint32_t g[4] = {gv[c].x, gv[c].y, gv[c].z, gv[c].w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float lo = __uint_as_float(w[q] << 16), hi = __uint_as_float(w[q] & 0xffff0000u);
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+            amax2 = __hmax2(amax2, __habs2(v));
             if (norm) {
-              const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
               const __nv_bfloat162 sq = __hmul2(v, v);
               const uint32_t su = *reinterpret_cast<const uint32_t*>(&sq);
               ss += __uint_as_float(su << 16) + __uint_as_float(su & 0xffff0000u);
-              const float glo = __uint_as_float(g[q] << 16), ghi = __uint_as_float(g[q] & 0xffff0000u);
-              mx = fmaxf(mx, fmaxf(fabsf(lo * glo), fabsf(hi * ghi)));
-            } else {
-              mx = fmaxf(mx, fmaxf(fabsf(lo), fabsf(hi)));
             }
           }
         }
       }
+      float mx = fmaxf(__low2float(amax2), __high2float(amax2));
+      float gm = fmaxf(__low2float(gmax2), __high2float(gmax2));
       ss = warp_sum(ss);
       mx = warp_max(mx);
-      if (lane == 0) { red[warp] = ss; red[8 + warp] = mx; }
+      if (norm) gm = warp_max(gm);
+      if (lane == 0) { red[warp] = ss; red[8 + warp] = mx; red[36 + warp] = gm; }
       named_bar_sync(1, NT);
-      ss = 0.f; mx = 0.f;
+      ss = 0.f; mx = 0.f; gm = 0.f;
 #pragma unroll
-      for (int w = 0; w < NCW; ++w) { ss += red[w]; mx = fmaxf(mx, red[8 + w]); }
+      for (int w = 0; w < NCW; ++w) { ss += red[w]; mx = fmaxf(mx, red[8 + w]); gm = fmaxf(gm, red[36 + w]); }
       float rinv = 1.f;
       if (norm) {
         rinv = rms_rinv(ss, p.K, p.eps);
-        mx = mx * rinv * 1.01f;     // |bf16(g * bf16(x * rinv))| <= |g x| rinv (1 + 2^-8)^2
+        mx = mx * gm * rinv * 1.01f;     // |bf16(g * bf16(x * rinv))| <= max|g| max|x| rinv (1 + 2^-8)^2
       }
       // 2^sh: the largest power of two with max|v| * 2^sh < 2^(8 NDIG - 2)
       const int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;   // mx < 2^(e + 1)
       int sh = (8 * NDIG - 3) - e;
       sh = max(-126, min(126, sh));
       const float scale = __uint_as_float((uint32_t)(sh + 127) << 23);
+      const float magic = __uint_as_float(MAGIC_BITS);
       const __nv_bfloat162 rinv2 = __float2bfloat162_rn(rinv);  // rinv is already a bf16 value
-      long long sx = 0;
+      uint32_t sxu = 0;     // sum of this thread's X (<= 48 values below 2^22), modulo 2^32
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) {
         const int k = (c * NT + tid) * 8;
@@ -244,14 +305,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
           uint32_t xd[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int X0 = __float2int_rn(__uint_as_float(w[q] << 16) * scale);          // exact product: power-of-two scale
-            const int X1 = __float2int_rn(__uint_as_float(w[q] & 0xffff0000u) * scale);
-            sx += (long long)X0 + (long long)X1;
-            xd[2 * q] = balanced_digits(X0);
-            xd[2 * q + 1] = balanced_digits(X1);
+            // x * 2^sh is exact in fp32 (8-bit significand, power-of-two scale): the fma rounds once, to nearest even,
+            // and leaves MAGIC_BITS + X in the result's bit pattern
+            const uint32_t b0 = __float_as_uint(__fmaf_rn(__uint_as_float(w[q] << 16), scale, magic));
+            const uint32_t b1 = __float_as_uint(__fmaf_rn(__uint_as_float(w[q] & 0xffff0000u), scale, magic));
+            sxu += b0 + b1;                                          // the 2 MAGIC_BITS per pair are removed below
+            xd[2 * q] = (b0 + (0x00808080u - MAGIC_BITS)) ^ 0x00808080u;      // balanced_digits(X); byte 3 is unused
+            xd[2 * q + 1] = (b1 + (0x00808080u - MAGIC_BITS)) ^ 0x00808080u;
           }
-          // 4 x 4 byte transposes: word (j, n) = digit n of elements 4j .. 4j+3  (B register j of lane t, column n)
-          uint32_t dj[2][4];
+          sxu -= 8u * MAGIC_BITS;
+          // 4 x 3 byte transposes: word (j, n) = digit n of elements 4j .. 4j+3  (B register j of lane t, column n)
+          uint32_t dj[2][3];
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const uint32_t lo01 = __byte_perm(xd[4 * j], xd[4 * j + 1], 0x5140), hi01 = __byte_perm(xd[4 * j], xd[4 * j + 1], 0x7362);
@@ -259,7 +323,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
             dj[j][0] = __byte_perm(lo01, lo23, 0x5410);
             dj[j][1] = __byte_perm(lo01, lo23, 0x7632);
             dj[j][2] = __byte_perm(hi01, hi23, 0x5410);
-            dj[j][3] = __byte_perm(hi01, hi23, 0x7632);
           }
           // k = 64 kb + 32 c32 + 8 t + (0..7): plane n, k block kb, lane slot t, words 2 c32, 2 c32 + 1
           uint8_t* dst = smem + L.xf + (k >> 6) * 64 + ((k >> 3) & 3) * 16 + ((k >> 5) & 1) * 8;
@@ -267,9 +330,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
           for (int n = 0; n < NDIG; ++n) *reinterpret_cast<uint2*>(dst + n * PS) = make_uint2(dj[0][n], dj[1][n]);
         }
       }
-      // exact sum of X over the row: int64 warp reduction, fixed-order sum of the 8 warp partials in the epilogue
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      // exact sum of X over the row: int32 inside groups of 8 lanes (8 x 48 x 2^22 < 2^31), int64 from there on;
+      // fixed-order sum of the 8 warp partials in the epilogue
+      int sxi = (int)sxu;
+      sxi += __shfl_xor_sync(0xffffffffu, sxi, 1);
+      sxi += __shfl_xor_sync(0xffffffffu, sxi, 2);
+      sxi += __shfl_xor_sync(0xffffffffu, sxi, 4);
+      long long sx = sxi;
+      sx += __shfl_xor_sync(0xffffffffu, sx, 8);
+      sx += __shfl_xor_sync(0xffffffffu, sx, 16);
       if (lane == 0) red_sx[warp] = sx;
       if (tid == 0) *red_sh = sh;
       named_bar_sync(3, NT + 32);          // releases the epilogue warp too: digit planes, sum X and sh are ready
@@ -364,6 +433,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
     if (tid == 0) tl_max(p.tl, 3);
   } else {
     // ===================== epilogue warp: lane = row of the 32-row unit =====================
+    if (p.pf_mode >= 2) {   // per-line variant of the L2 prefetch (this warp idles until the first unit is reduced)
+      const uint32_t step = p.pf_mode == 2 ? 128u : 32u;
+#pragma unroll
+      for (int sgi = 0; sgi < B2L_PF_SEGMENTS; ++sgi) {
+        if (p.pf_bytes[sgi] == 0) continue;
+        uint32_t lo, hi;
+        pf_slice(p.pf_bytes[sgi], lo, hi);
+#pragma unroll 1
+        for (uint32_t o = lo + lane * step; o < hi; o += 32 * step) l2_prefetch_line(p.pf_ptr[sgi] + o);
+      }
+    }
     pdl_wait();
     const long long* red_sx = reinterpret_cast<const long long*>(smem + L.red + 64);
     const int* red_sh = reinterpret_cast<const int*>(smem + L.red + 128);
@@ -551,13 +631,28 @@ extern "C" int b2l_q4_gemv(const b2l_q4_linear_args* a, b2l_stream_t stream) {
   p.nst = 0;
   p.tl = (unsigned long long*)a->trace;
   p.nocompute = (a->flags & B2L_F_DEBUG_NOCOMPUTE) ? 1 : 0;
+  // L2 prefetch hint.  B2L_PF_MODE (read once): 0 ignores the hint, 1 (default) bulk prefetch, 2 / 4 per-line prefetch;
+  // B2L_PF_EVICT=1 marks the demand loads evict_first
+  static const int env_pf_mode = [] { const char* e = getenv("B2L_PF_MODE"); return e ? atoi(e) : 1; }();
+  static const int env_evict = [] { const char* e = getenv("B2L_PF_EVICT"); return e ? atoi(e) : 0; }();
+  p.pf_mode = 0;
+  p.evict_first = env_evict;
+  for (int i = 0; i < B2L_PF_SEGMENTS; ++i) {
+    p.pf_ptr[i] = (const uint8_t*)a->pf_ptr[i];
+    p.pf_bytes[i] = 0;
+    if (a->pf_ptr[i] != nullptr && a->pf_bytes[i] != 0) {
+      B2L_CHECK_ARG(((uintptr_t)a->pf_ptr[i] % 16 == 0) && (a->pf_bytes[i] % 16 == 0) && a->pf_bytes[i] < (1ull << 31),
+                    "b2l_q4_gemv: prefetch segment %d must be 16-byte aligned, a multiple of 16 and < 2 GiB", i);
+      p.pf_bytes[i] = (uint32_t)a->pf_bytes[i];
+      p.pf_mode = env_pf_mode;
+    }
+  }
   // tuning knob (read once): B2L_GEMV_CTAS_PER_SM (default 2; K > 16384 runs one CTA per SM with a deeper ring)
   static const int env_cps = [] { const char* e = getenv("B2L_GEMV_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   const bool pdl = (a->flags & B2L_F_PDL) != 0;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = a->split_k;  // split_k doubles as a grid override
-  // four digits (|X| < 2^30) while the digit planes leave room for >= 4 ring stages, else three (|X| < 2^22)
-  if (a->K <= 8192) return launch_gemv<6, 4>(p, env_cps > 0 ? env_cps : 2, grid, pdl, st);
+  // three digits (|X| < 2^22) everywhere: the prologue's fma conversion needs the integer inside a float mantissa
   if (a->K <= 12288) return launch_gemv<6, 3>(p, env_cps > 0 ? env_cps : 2, grid, pdl, st);
   if (a->K <= 16384) return launch_gemv<12, 3>(p, env_cps > 0 ? env_cps : 2, grid, pdl, st);
   return launch_gemv<12, 3>(p, 1, grid, pdl, st);
