@@ -115,6 +115,14 @@ typedef struct b2l_q4_linear_args {
                            activations, reduces and writes its result (the reference has no counterpart:
                            quantization.py:284-333 launches one Triton kernel per linear)          */
   unsigned long long pf_bytes[B2L_PF_SEGMENTS];
+  /* strided form of the same hint - the KV-cache rows a later b2l_attention launch reads (model.py:211-222):
+     pf_nseg ranges, pf_seg_stride bytes apart, at each of pf_kv[0] and pf_kv[1]; every range is
+     rows * pf_row_bytes bytes long, rows = min(*pf_rows, pf_rows_max) read ON THE DEVICE when the launch runs
+     (pf_rows = the step's input_pos).  pf_kv[0] == NULL: unused                                           */
+  const void* pf_kv[2];
+  const long long* pf_rows;
+  int pf_rows_max, pf_nseg, pf_row_bytes;
+  unsigned long long pf_seg_stride;
 } b2l_q4_linear_args;
 
 enum {

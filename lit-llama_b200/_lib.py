@@ -27,6 +27,8 @@ class Q4LinearArgs(C.Structure):
         ("epilogue", c_int), ("res", c_void_p), ("ldres", c_int),
         ("split_k", c_int), ("flags", c_int), ("trace", c_void_p), ("workspace", c_void_p),
         ("pf_ptr", c_void_p * 4), ("pf_bytes", C.c_ulonglong * 4),
+        ("pf_kv", c_void_p * 2), ("pf_rows", c_void_p), ("pf_rows_max", c_int), ("pf_nseg", c_int), ("pf_row_bytes", c_int),
+        ("pf_seg_stride", C.c_ulonglong),
     ]
 
 

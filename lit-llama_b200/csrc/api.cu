@@ -119,8 +119,16 @@ static std::vector<PfWindow> prefetch_windows(const b2l_decode_args* d) {
 
 static int q4_call(const b2l_q4_weight& w, const void* x, int ldx, void* y, int ldy, int M, int sz_dtype, int prologue,
                    const void* norm_scale, float eps, int epilogue, const void* res, int ldres, int flags,
-                   b2l_stream_t stream, void* trace = nullptr, void* batch_work = nullptr, const PfWindow* pf = nullptr) {
+                   b2l_stream_t stream, void* trace = nullptr, void* batch_work = nullptr, const PfWindow* pf = nullptr,
+                   const b2l_decode_args* kv_of = nullptr, int kv_layer = 0) {
   b2l_q4_linear_args a{};
+  if (kv_of != nullptr) {   // this linear also asks the L2 for the KV-cache rows of layer `kv_layer`'s attention
+    const int hs = kv_of->n_embd / kv_of->n_head;
+    a.pf_kv[0] = kv_of->layers[kv_layer].k_cache; a.pf_kv[1] = kv_of->layers[kv_layer].v_cache;
+    a.pf_rows = (const long long*)kv_of->input_pos;
+    a.pf_rows_max = kv_of->S; a.pf_nseg = kv_of->B * kv_of->n_head; a.pf_row_bytes = hs * 2;
+    a.pf_seg_stride = (unsigned long long)kv_of->S * hs * 2;
+  }
   if (pf != nullptr)
     for (int i = 0; i < B2L_PF_SEGMENTS; ++i) { a.pf_ptr[i] = pf->ptr[i]; a.pf_bytes[i] = pf->bytes[i]; }
   a.x = x; a.ldx = ldx;
@@ -174,6 +182,9 @@ extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {
   // batch 1 on the int8-MMA kernel: every linear carries the L2 prefetch window of the weights that follow it
   std::vector<PfWindow> pfw;
   if (B == 1 && d->lm_head.qw_mma != nullptr) pfw = prefetch_windows(d);
+  // B2L_KV_PREFETCH (read once): 0 off, 1 the previous Block's mlp.c_proj asks for a Block's KV rows, 2 its own c_attn does
+  static const int kv_prefetch = [] { const char* e = getenv("B2L_KV_PREFETCH"); return e ? atoi(e) : 0; }();
+  const bool kv_ok = B == 1 && hs == 128 && d->lm_head.qw_mma != nullptr;
   int oi = 0;
   auto pf = [&]() -> const PfWindow* { const PfWindow* r = pfw.empty() ? nullptr : &pfw[oi]; ++oi; return r; };
   if ((rc = b2l_ring_advance(d->input_pos, 1, d->ring_start, d->S, stream))) return rc;
@@ -181,7 +192,7 @@ extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {
   for (int l = 0; l < d->n_layer; ++l) {
     const b2l_layer& L = d->layers[l];
     if ((rc = q4_call(L.c_attn, d->x, C, d->qkv, 3 * C, B, d->sz_dtype, B2L_PRO_RMSNORM, L.rms_1, d->eps, B2L_EPI_STORE,
-                      nullptr, 0, fl, stream, tl(), d->batch_work, pf())))
+                      nullptr, 0, fl, stream, tl(), d->batch_work, pf(), (kv_ok && kv_prefetch == 2) ? d : nullptr, l)))
       return rc;
     g_attn_timeline = tl();
     if ((rc = b2l_attention(d->qkv, L.k_cache, L.v_cache, d->rope, d->input_pos, d->ring_start, d->att, d->attn_work, B,
@@ -196,8 +207,11 @@ extern "C" int b2l_decode_step(const b2l_decode_args* d, b2l_stream_t stream) {
     if ((rc = q4_call(L.c_fc12, d->x, C, d->hid, d->n_hidden, B, d->sz_dtype, B2L_PRO_RMSNORM, L.rms_2, d->eps,
                       B2L_EPI_SWIGLU, nullptr, 0, fl, stream, tl(), d->batch_work, pf())))
       return rc;
+    // mlp.c_proj fits the weight ring entirely, so HBM idles while it converts its activations: it asks the L2 for
+    // the NEXT Block's KV-cache rows (B2L_KV_PREFETCH=0 switches that off)
+    const bool kvpf = kv_prefetch == 1 && kv_ok && l + 1 < d->n_layer;
     if ((rc = q4_call(L.mlp_proj, d->hid, d->n_hidden, d->x, C, B, d->sz_dtype, B2L_PRO_NONE, nullptr, 0.f,
-                      B2L_EPI_RESIDUAL, d->x, C, fl, stream, tl(), d->batch_work, pf())))
+                      B2L_EPI_RESIDUAL, d->x, C, fl, stream, tl(), d->batch_work, pf(), kvpf ? d : nullptr, l + 1)))
       return rc;
   }
   return q4_call(d->lm_head, d->x, C, d->logits, d->vocab, B, d->sz_dtype, B2L_PRO_RMSNORM, d->ln_f, d->eps,

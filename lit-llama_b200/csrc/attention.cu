@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
                              __nv_bfloat16* __restrict__ v_cache, const float* __restrict__ rope,
                              const int64_t* __restrict__ input_pos, const int32_t* __restrict__ ring_start,
                              __nv_bfloat16* __restrict__ y, float* __restrict__ work, int* __restrict__ tickets,
-                             int n_head, int S, int block_size, int n_split, unsigned long long* tl) {
+                             int n_head, int S, int block_size, int n_split, unsigned long long* tl, int pre_tiles) {
   constexpr int HS = 128;
   extern __shared__ __align__(128) uint8_t fsm[];
   float* sm_acc = reinterpret_cast<float*>(fsm + 4 * FD_SUB_BYTES);                // [FD_WARPS][HS]
@@ -255,6 +255,11 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
 
   if (threadIdx.x == 0) tl_min(tl, 0);
   const int bh = blockIdx.x, b = bh / n_head, h = bh % n_head, sp = blockIdx.y;
+  // debug: raw stamps of CTA (0, 0) in slots 8.. (start, wait done, q ready, per sub-tile: data seen / done, merged, end)
+  unsigned long long* tl0 = (tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ? tl + 8 : nullptr;
+  int tli = 0;
+  auto stamp = [&]() { if (tl0 != nullptr && tli < 24) tl0[tli++] = globaltimer_ns(); };
+  stamp();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = n_head * HS;
   const size_t head_base = ((size_t)b * n_head + h) * S * HS;
@@ -296,13 +301,14 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
       fd_bulk(vd + first * HS * 2, v_cache + head_base, (uint32_t)(cnt - first) * HS * 2, bar);
     }
   };
-  // ---- before the dependency: the first two sub-tiles
+  // ---- before the dependency: the first sub-tile (both when one CTA per head is all there is: nothing queues then)
+  const int pre = (n_active == 1) ? 2 : pre_tiles;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (n_sub > 0) request(0);
-    if (n_sub > 1) request(1);
+    if (pre > 1 && n_sub > 1) request(1);
   }
   // the RoPE row of this position is a constant table entry: fetch it before the dependency too
   const long long prow = p < block_size ? p : (long long)block_size - 1;
@@ -319,6 +325,7 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   __syncthreads();  // the barriers are initialised before anyone polls them
   pdl_wait();
   if (threadIdx.x == 0) tl_max(tl, 1);
+  stamp();
   pdl_launch_dependents();  // attn.c_proj may start streaming its weights
 
   const __nv_bfloat16* qrow = qkv + (size_t)b * 3 * C + h * HS + d0;
@@ -326,8 +333,13 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   {
     float raw[16];
     // qkv is the output of the kernel this one was launched behind (PDL): coherent loads only
-    bf16x8_to_f32(ld_coherent_u4(qrow), raw);
-    bf16x8_to_f32(ld_coherent_u4(qrow + 8), raw + 8);
+    const uint4 qa = ld_coherent_u4(qrow), qb = ld_coherent_u4(qrow + 8);
+    // The second sub-tile is requested BEHIND the q loads: a reply to this SM queues behind the bulk data already
+    // on its way (measured, tools/diag.py timeline: with two 32 KB sub-tiles per CTA in flight the 32-byte q load
+    // came back after 2.4 us at position 1033, 0.5 us with one), and q is what the first score needs.
+    if (threadIdx.x == 0 && pre <= 1 && n_sub > 1) request(1);
+    bf16x8_to_f32(qa, raw);
+    bf16x8_to_f32(qb, raw + 8);
     const float scale = rsqrtf((float)HS);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -342,49 +354,9 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   float m = -INFINITY, l = 0.f, acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  // ---- old rows, sub-tile by sub-tile: warp w takes rows 8 w .. 8 w + 7 (4 keys per round, 8 lanes per key)
-  for (int i = 0; i < n_sub; ++i) {
-    const int buf = i & 1;
-    const int cnt = min(FD_SUB, n_old - i * FD_SUB);
-    {
-      uint32_t ok;
-      const uint32_t par = (uint32_t)(i >> 1) & 1u;
-      do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar0 + buf * 8), "r"(par) : "memory");
-      } while (!ok);
-    }
-    const __nv_bfloat16* kt = reinterpret_cast<const __nv_bfloat16*>(fsm + buf * 2 * FD_SUB_BYTES);
-    const __nv_bfloat16* vt = kt + FD_SUB * HS;
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int r = warp * 8 + it * 4 + grp;
-      const bool valid = r < cnt;
-      const int rc = valid ? r : 0;
-      const uint4* kr = reinterpret_cast<const uint4*>(kt + (size_t)rc * HS + d0);
-      const uint4* vr = reinterpret_cast<const uint4*>(vt + (size_t)rc * HS + d0);
-      float kf[16], vf[16];
-      bf16x8_to_f32(kr[0], kf); bf16x8_to_f32(kr[1], kf + 8);
-      float sc = 0.f;
-#pragma unroll
-      for (int e = 0; e < 16; ++e) sc = fmaf(q[e], kf[e], sc);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-      if (valid) {
-        bf16x8_to_f32(vr[0], vf); bf16x8_to_f32(vr[1], vf + 8);
-        const float mn = fmaxf(m, sc);
-        const float corr = __expf(m - mn), pj = __expf(sc - mn);
-        l = l * corr + pj;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) acc[e] = fmaf(pj, vf[e], acc[e] * corr);
-        m = mn;
-      }
-    }
-    __syncthreads();   // every warp is done with this buffer
-    if (threadIdx.x == 0 && i + 2 < n_sub) request(i + 2);
-  }
-  if (threadIdx.x == 0) tl_max(tl, 2);
-  // ---- the new token: rotate k, append k and v to the cache, score from registers (warp 0, key group 0)
+  if (tl0 != nullptr && q[0] != 12345.678f) stamp();   // q ready (the comparison keeps the stamp behind the loads)
+  // ---- the new token FIRST (its k / v loads travel with the q loads, while the old tiles are still landing):
+  // rotate k, append k and v to the cache, score from registers (warp 0, key group 0)
   if (has_new && warp == 0 && grp == 0) {
     int phys = w_slot + ring; if (phys >= S) phys -= S;
     float raw[16], kf[16], vf[16];
@@ -417,6 +389,63 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
     for (int e = 0; e < 16; ++e) acc[e] = fmaf(pj, vf[e], acc[e] * corr);
     m = mn;
   }
+  // ---- old rows, sub-tile by sub-tile: warp w takes rows 8 w .. 8 w + 7 (4 keys per round, 8 lanes per key)
+  for (int i = 0; i < n_sub; ++i) {
+    const int buf = i & 1;
+    const int cnt = min(FD_SUB, n_old - i * FD_SUB);
+    {
+      uint32_t ok;
+      const uint32_t par = (uint32_t)(i >> 1) & 1u;
+      do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar0 + buf * 8), "r"(par) : "memory");
+      } while (!ok);
+    }
+    const __nv_bfloat16* kt = reinterpret_cast<const __nv_bfloat16*>(fsm + buf * 2 * FD_SUB_BYTES);
+    const __nv_bfloat16* vt = kt + FD_SUB * HS;
+    stamp();
+    // the warp's 8 keys of this sub-tile as two groups of 4 (8 lanes per key): both scores first (independent chains),
+    // ONE running-max update, then both value rows -- half the dependent (m, l, acc) updates of a key-by-key loop
+    float sc[2];
+    bool valid[2];
+    const uint4* vr[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int r = warp * 8 + it * 4 + grp;
+      valid[it] = r < cnt;
+      const int rc = valid[it] ? r : 0;
+      const uint4* kr = reinterpret_cast<const uint4*>(kt + (size_t)rc * HS + d0);
+      vr[it] = reinterpret_cast<const uint4*>(vt + (size_t)rc * HS + d0);
+      float kf[16];
+      bf16x8_to_f32(kr[0], kf); bf16x8_to_f32(kr[1], kf + 8);
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a0 = fmaf(q[e], kf[e], a0); a1 = fmaf(q[8 + e], kf[8 + e], a1); }
+      sc[it] = a0 + a1;
+    }
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1) {
+      sc[0] += __shfl_xor_sync(0xffffffffu, sc[0], o);
+      sc[1] += __shfl_xor_sync(0xffffffffu, sc[1], o);
+    }
+    {
+      const float s0 = valid[0] ? sc[0] : -INFINITY, s1 = valid[1] ? sc[1] : -INFINITY;
+      const float mn = fmaxf(m, fmaxf(s0, s1));
+      if (mn != -INFINITY) {   // at least one key so far in this lane group
+        const float corr = __expf(m - mn), p0 = __expf(s0 - mn), p1 = __expf(s1 - mn);   // exp(-inf) = 0
+        float v0[16], v1[16];
+        bf16x8_to_f32(vr[0][0], v0); bf16x8_to_f32(vr[0][1], v0 + 8);
+        bf16x8_to_f32(vr[1][0], v1); bf16x8_to_f32(vr[1][1], v1 + 8);
+        l = l * corr + p0 + p1;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = fmaf(p1, v1[e], fmaf(p0, v0[e], acc[e] * corr));
+        m = mn;
+      }
+    }
+    __syncthreads();   // every warp is done with this buffer
+    stamp();
+    if (threadIdx.x == 0 && i + 2 < n_sub) request(i + 2);
+  }
+  if (threadIdx.x == 0) tl_max(tl, 2);
   __syncwarp();
   if (threadIdx.x == 0) tl_max(tl, 3);
   // merge the 4 key groups of the warp (lanes with the same `sub` hold the same dims)
@@ -457,9 +486,11 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
 #pragma unroll
   for (int w = 0; w < FD_WARPS; ++w) a += sm_acc[w * HS + d] * wgt[w];
 
+  stamp();
   if (n_active == 1) {  // nothing to merge
     if (writer) y[(size_t)b * C + h * HS + d] = f2bf(a / Ls);
     if (threadIdx.x == 0) tl_max(tl, 4);
+    stamp();
     return;
   }
   float* out = work + ((size_t)bh * n_split + sp) * (HS + 2);
@@ -473,6 +504,7 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
     if (sm_last) tickets[bh] = 0;  // every contributor has arrived: safe to re-arm for the next step
   }
   __syncthreads();  // thread 0's acquire + this barrier order the other CTAs' partials before the loads below
+  stamp();
   if (!sm_last) return;
   // merge: every load is issued before the first use (n_split <= 8 for S <= 2048; larger S loops in batches)
   const float* base = work + (size_t)bh * n_split * (HS + 2);
@@ -774,11 +806,13 @@ extern "C" int b2l_attention(void* qkv, void* k_cache, void* v_cache, const void
     const int n_split = (S + FD_SUB - 1) / FD_SUB;
     int* tickets = reinterpret_cast<int*>(reinterpret_cast<char*>(work) + ws_partials_bytes(B, n_head, head_size, T, S));
     static DynSmemCache smem_cache;
+    // B2L_ATTN_PRE (read once): sub-tiles requested before griddepcontrol.wait, 1 (default) or 2
+    static const int env_pre = [] { const char* e = getenv("B2L_ATTN_PRE"); return e ? atoi(e) : 1; }();
     if (int rc = ensure_dyn_smem(attn_decode_fused_kernel, FD_SMEM_BYTES, smem_cache)) return rc;
     LaunchCfg lc(dim3(B * n_head, n_split), dim3(FD_WARPS * 32), FD_SMEM_BYTES, st, (flags & B2L_F_PDL) != 0);
     B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, attn_decode_fused_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_cache,
                                 (__nv_bfloat16*)v_cache, (const float*)rope, input_pos, ring_start, (__nv_bfloat16*)y,
-                                (float*)work, tickets, n_head, S, block_size, n_split, (unsigned long long*)g_attn_timeline));
+                                (float*)work, tickets, n_head, S, block_size, n_split, (unsigned long long*)g_attn_timeline, env_pre));
     return 0;
   }
   int rt = head_size / 2 < 32 ? 32 : head_size / 2;

@@ -60,6 +60,8 @@ struct Params {
   const uint8_t* pf_ptr[B2L_PF_SEGMENTS];
   uint32_t pf_bytes[B2L_PF_SEGMENTS];
   int pf_mode;             // 0 off, 1 bulk prefetch by the producer lane, 2 / 4 per-line prefetch (128 B / 32 B apart)
+  // strided form (KV-cache rows of a following attention launch; b2l_q4_linear_args::pf_kv)
+  const uint8_t* pf_kv[2]; const long long* pf_rows; int pf_rows_max, pf_nseg, pf_row_bytes; unsigned long long pf_seg_stride;
   int evict_first;         // demand loads carry an L2 evict_first policy (a weight byte is read once per token)
 };
 
@@ -70,7 +72,7 @@ __host__ __device__ inline uint32_t plane_stride(int K) { return (uint32_t)K + (
 
 // shared memory map
 struct SmemLayout {
-  uint32_t ring, xf, zero, scratch, red, bars, total;
+  uint32_t ring, xf, zero, scratch, red, sxp, bars, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int nst, int K, int ndig) {
   SmemLayout L;
@@ -80,6 +82,7 @@ __host__ __device__ inline SmemLayout smem_layout(int nst, int K, int ndig) {
   L.zero = o;    o += 16;                                 // the B operand of the unused MMA columns
   L.scratch = o; o += 2 * NCW * MAX_HALVES * RB * 16;     // [buf][warp][half][row][digit (4)] int32 partials
   L.red = o;     o += 192;                                // reductions: float[8] sumsq, float[8] max, int64[8] sum X, int sh, float[8] max|g|
+  L.sxp = o;     o += NCW * 32 * 4;                       // per-thread partial sums of X
   L.bars = o;    o += 2 * MAX_STAGES * 8;
   L.total = (o + 127u) & ~127u;
   return L;
@@ -201,11 +204,28 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
         }
       }
       if (total_stages == 0) pdl_launch_dependents();
+      if (p.pf_kv[0] != nullptr) {
+        // KV-cache rows of the attention launch that follows the next linear: requested once this CTA's own ring is
+        // full (behind its demand loads), 16 KB per instruction, round-robin over the grid.  The cache rows of old
+        // positions do not depend on the current token; the attention kernel can only start its own loads when the
+        // linear before it frees shared memory, so without this the cache streams from HBM on the critical path.
+        long long rows = *p.pf_rows;
+        rows = rows < 0 ? 0 : (rows > p.pf_rows_max ? p.pf_rows_max : rows);
+        const uint32_t seg_bytes = (uint32_t)rows * (uint32_t)p.pf_row_bytes;
+        const uint32_t cps = (seg_bytes + PF_CHUNK - 1) / PF_CHUNK;
+        const uint32_t total = 2u * (uint32_t)p.pf_nseg * cps;
+#pragma unroll 1
+        for (uint32_t id = blockIdx.x; id < total; id += gridDim.x) {
+          const uint32_t sg = id / cps, o = (id - sg * cps) * PF_CHUNK;
+          const uint32_t which = sg >= (uint32_t)p.pf_nseg ? 1u : 0u;
+          const uint8_t* base = p.pf_kv[which] + (size_t)(sg - which * p.pf_nseg) * p.pf_seg_stride;
+          l2_prefetch_bulk(base + o, min(PF_CHUNK, seg_bytes - o));
+        }
+      }
     }
   } else if (warp < NCW) {
     // ===================== consumer warps =====================
     float* red = reinterpret_cast<float*>(smem + L.red);   // [0..7] sum of squares, [8..15] max, then int64[8] sum X, int sh
-    long long* red_sx = reinterpret_cast<long long*>(smem + L.red + 64);
     int* red_sh = reinterpret_cast<int*>(smem + L.red + 128);
     // ---- activations: [RMSNorm], power-of-two scaling, balanced digits in B-fragment order, exact sum(X).
     // Every CTA converts the whole row (K values, 296 times per launch), and the launch cannot start its main loop
@@ -233,6 +253,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) gmax2 = __hmax2(gmax2, __habs2(*reinterpret_cast<const __nv_bfloat162*>(&g[q])));
         }
+        const float gw = warp_max(fmaxf(__low2float(gmax2), __high2float(gmax2)));
+        if (lane == 0) red[36 + warp] = gw;      // read after the pass-1 barrier below
       }
       pdl_wait();
       if (tid == 0) tl_max(p.tl, 1);
@@ -265,15 +287,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
         }
       }
       float mx = fmaxf(__low2float(amax2), __high2float(amax2));
-      float gm = fmaxf(__low2float(gmax2), __high2float(gmax2));
       ss = warp_sum(ss);
       mx = warp_max(mx);
-      if (norm) gm = warp_max(gm);
-      if (lane == 0) { red[warp] = ss; red[8 + warp] = mx; red[36 + warp] = gm; }
+      if (lane == 0) { red[warp] = ss; red[8 + warp] = mx; }
       named_bar_sync(1, NT);
-      ss = 0.f; mx = 0.f; gm = 0.f;
+      float gm = 0.f;
+      ss = 0.f; mx = 0.f;
 #pragma unroll
-      for (int w = 0; w < NCW; ++w) { ss += red[w]; mx = fmaxf(mx, red[8 + w]); gm = fmaxf(gm, red[36 + w]); }
+      for (int w = 0; w < NCW; ++w) { ss += red[w]; mx = fmaxf(mx, red[8 + w]); if (norm) gm = fmaxf(gm, red[36 + w]); }
       float rinv = 1.f;
       if (norm) {
         rinv = rms_rinv(ss, p.K, p.eps);
@@ -330,16 +351,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
           for (int n = 0; n < NDIG; ++n) *reinterpret_cast<uint2*>(dst + n * PS) = make_uint2(dj[0][n], dj[1][n]);
         }
       }
-      // exact sum of X over the row: int32 inside groups of 8 lanes (8 x 48 x 2^22 < 2^31), int64 from there on;
-      // fixed-order sum of the 8 warp partials in the epilogue
-      int sxi = (int)sxu;
-      sxi += __shfl_xor_sync(0xffffffffu, sxi, 1);
-      sxi += __shfl_xor_sync(0xffffffffu, sxi, 2);
-      sxi += __shfl_xor_sync(0xffffffffu, sxi, 4);
-      long long sx = sxi;
-      sx += __shfl_xor_sync(0xffffffffu, sx, 8);
-      sx += __shfl_xor_sync(0xffffffffu, sx, 16);
-      if (lane == 0) red_sx[warp] = sx;
+      // exact sum of X over the row: every thread leaves its int32 partial (<= 48 values below 2^22) in shared memory
+      // and goes on to the main loop; the epilogue warp, idle until the first unit is done, adds the 256 partials
+      // in int64 (integers: the order does not matter)
+      reinterpret_cast<int*>(smem + L.sxp)[tid] = (int)sxu;
       if (tid == 0) *red_sh = sh;
       named_bar_sync(3, NT + 32);          // releases the epilogue warp too: digit planes, sum X and sh are ready
       if (tid == 0) tl_max(p.tl, 2);
@@ -445,13 +460,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) q4_gemv_kernel(const Params p) {
       }
     }
     pdl_wait();
-    const long long* red_sx = reinterpret_cast<const long long*>(smem + L.red + 64);
     const int* red_sh = reinterpret_cast<const int*>(smem + L.red + 128);
     const int* scratch = reinterpret_cast<const int*>(smem + L.scratch);
     named_bar_sync(3, NCW * 32 + 32);
     long long sum_x = 0;
+    {
+      const int4* sp = reinterpret_cast<const int4*>(smem + L.sxp) + lane * 2;   // 8 partials per lane
+      const int4 s0 = sp[0], s1 = sp[1];
+      sum_x = (long long)s0.x + s0.y + s0.z + s0.w + s1.x + s1.y + s1.z + s1.w;
 #pragma unroll
-    for (int w = 0; w < NCW; ++w) sum_x += red_sx[w];
+      for (int o = 16; o > 0; o >>= 1) sum_x += __shfl_xor_sync(0xffffffffu, sum_x, o);
+    }
     const double dsum_x = (double)sum_x;
     const int sh = *red_sh;
     const double inv_scale = __longlong_as_double((long long)(1023 - sh) << 52);   // 2^-sh
@@ -637,6 +656,16 @@ extern "C" int b2l_q4_gemv(const b2l_q4_linear_args* a, b2l_stream_t stream) {
   static const int env_evict = [] { const char* e = getenv("B2L_PF_EVICT"); return e ? atoi(e) : 0; }();
   p.pf_mode = 0;
   p.evict_first = env_evict;
+  p.pf_kv[0] = p.pf_kv[1] = nullptr; p.pf_rows = nullptr; p.pf_rows_max = p.pf_nseg = p.pf_row_bytes = 0; p.pf_seg_stride = 0;
+  if (a->pf_kv[0] != nullptr) {
+    B2L_CHECK_ARG(a->pf_kv[1] != nullptr && a->pf_rows != nullptr && a->pf_rows_max > 0 && a->pf_nseg > 0 && a->pf_row_bytes > 0 &&
+                      a->pf_row_bytes % 16 == 0 && a->pf_seg_stride % 16 == 0 && ((uintptr_t)a->pf_kv[0] % 16 == 0) &&
+                      ((uintptr_t)a->pf_kv[1] % 16 == 0) && (unsigned long long)a->pf_rows_max * a->pf_row_bytes < (1ull << 31),
+                  "b2l_q4_gemv: bad strided prefetch hint");
+    p.pf_kv[0] = (const uint8_t*)a->pf_kv[0]; p.pf_kv[1] = (const uint8_t*)a->pf_kv[1];
+    p.pf_rows = a->pf_rows; p.pf_rows_max = a->pf_rows_max; p.pf_nseg = a->pf_nseg; p.pf_row_bytes = a->pf_row_bytes;
+    p.pf_seg_stride = a->pf_seg_stride;
+  }
   for (int i = 0; i < B2L_PF_SEGMENTS; ++i) {
     p.pf_ptr[i] = (const uint8_t*)a->pf_ptr[i];
     p.pf_bytes[i] = 0;

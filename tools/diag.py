@@ -954,6 +954,9 @@ def sec_timeline():
                 extra = ""
                 if li % 5 != 1:
                     extra = f"  | x_ready min..max {int(t[li, 60]) - base}..{r[2]}  loop_done min..max {int(t[li, 61]) - base}..{r[3]}"
+                if li % 5 == 1:
+                    b1 = int(t[li, 0])
+                    extra = "  | CTA(0,0): " + " ".join(str(int(t[li, 8 + i]) - b1) for i in range(24) if int(t[li, 8 + i]))
                 print(f"  L{li // 5} {names[li % 5]:9s} {r}{extra}")
             for li in (20, 23):  # layer 4 c_attn and fc12: CTA 0 per-stage stamps
                 b0 = int(t[li, 0])
