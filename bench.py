@@ -18,8 +18,10 @@ positions 16..2047 whatever K is (a stride, not consecutive positions), so `valu
             __graft_entry__.build()) on the host cores, same synthetic weights as the GPU arm, whole tokens through
             all 32 Blocks; the token loop is the golden-pinned restatement of generate.py (oracle/llama_oracle.py).
             Fallback when oracle/_ref is absent: the oracle port (kind "port").
-N > 1: independent replicas, one process per GPU (the reference has no multi-GPU inference, SURVEY.md section 2.1);
-weak scaling, no data-path collective.  The tensor-parallel path is measured by tools/tp_bench.py.
+N > 1: `value` = independent replicas, one process per GPU (the reference has no multi-GPU inference, SURVEY.md section
+2.1; 7B fits one GPU): weak scaling, no data-path collective.  The same run then measures the TENSOR-PARALLEL path on
+the same ranks and reports it under "tp": LLaMA-7B split N ways, and LLaMA-65B gptq.int4 TP = 8 (BASELINE.json
+configs[4]) when N = 8 -- fused per-rank step, two one-shot all-reduces per Block over peer memory (tools/tp_bench.py).
 """
 import argparse
 import json
@@ -322,6 +324,44 @@ def time_q4_launches(model, dev):
     return e0.elapsed_time(e1) / reps * 1e-3, len(calls), ("q4_gemv_kernel" if gemv else "q4_linear_tc_kernel")
 
 
+def build_line(args, world, K, warm, t_dev, t_e2e, Ke, timed_pos, points, clk, t_q4, n_q4, q4_name, launches, lo):
+    """The JSON line of the `ours` arm (rank 0)."""
+    W, kv = model_bytes(MODEL)
+    mean_p = sum(timed_pos) / K
+    bytes_per_token = W + kv * (mean_p + 1) + kv
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    ach = W / t_q4 / 1e9
+    traffic = None
+    try:  # dram bytes of the kernel's launches of one token, from the committed ncu capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["bytes_per_token"]
+    except (OSError, KeyError, ValueError):
+        pass
+    return {
+        "metric": "LLaMA-7B gptq.int4 decode tokens/sec", "value": aggregate_throughput(world, K, t_dev), "unit": "tokens/s", "n_gpus": world,
+        "steps": K, "warmup": warm, "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "LLaMA-7B gptq.int4 decode batch=1 ctx=2048 (random-init weights)", "prompt_tokens": PROMPT_T,
+                   "positions": f"{K} positions spread evenly over {lo}..{S_CTX - 1} (mean {mean_p:.0f})",
+                   "points": {**points, "unit": "tokens/s at fixed position"}, "sampling": f"top_k={TOP_K} temperature={TEMPERATURE}",
+                   "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                   "l2": "weights 3.31 GB per token >> 126 MB L2 (inputs larger than L2)"},
+        "clocks": clk,
+        "e2e": {"value": aggregate_throughput(world, Ke, t_e2e), "unit": "tokens/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 8, "steps": Ke},
+        "gpu_launches": (launches + 1) * K,  # b2l_decode_step's kernels + the fused sampling kernel, per token
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                     "kernel": q4_name, "launches_per_token": n_q4, "bytes_per_token_launches": W,
+                     "peak_source": which,
+                     "whole_token_bytes": bytes_per_token, "whole_token_achieved": bytes_per_token * K / t_dev / 1e9,
+                     "whole_token_frac": bytes_per_token * K / t_dev / 1e9 / peak},
+    }
+
+
 def reduce_max(times, device):
     """Max over ranks of per-rank times (the N > 1 rule of the bench contract).  Replicas
     share nothing else: there is no data-path collective."""
@@ -346,6 +386,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tp", action="store_true", help="N > 1: skip the tensor-parallel block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -443,52 +484,58 @@ def main():
 
     t_dev, t_e2e = reduce_max([t_dev, t_e2e], dev)
 
-    if rank == 0:
-        W, kv = model_bytes(MODEL)
-        mean_p = sum(timed_pos) / K
-        bytes_per_token = W + kv * (mean_p + 1) + kv
-        peaks = {}
+    from lit_llama_b200 import _lib as L
+    import ctypes as C
+    launches = L.lib().b2l_decode_step_launches(C.byref(model._decode.args))
+
+    # ---- N > 1: the tensor-parallel path on the same ranks (`value` stays the replicas metric).
+    # 7B split N ways, and LLaMA-65B gptq.int4 TP = 8 (BASELINE.json configs[4]) when N = 8.  A watchdog ends the run with
+    # the headline line intact should a collective ever hang.
+    tp = None
+    if world > 1 and not args.no_tp:
+        del model
+        torch.cuda.empty_cache()
+        box = {"line": None}
+
+        def bail():
+            if rank == 0 and box["line"] is not None:
+                box["line"]["tp"] = {"error": "tensor-parallel block did not finish within its time limit"}
+                print(json.dumps(box["line"]), flush=True)
+            os._exit(0)
+
+        watchdog = threading.Timer(float(os.environ.get("B2L_TP_BENCH_LIMIT_S", "420")), bail)
+        watchdog.daemon = True
+        if rank == 0:
+            box["line"] = build_line(args, world, K, warm, t_dev, t_e2e, Ke, timed_pos, points, clk, t_q4, n_q4, q4_name, launches, lo)
+        watchdog.start()
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        ach = W / t_q4 / 1e9
-        traffic = None
-        try:  # dram bytes of the kernel's launches of one token, from the committed ncu capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["bytes_per_token"]
-        except (OSError, KeyError, ValueError):
-            pass
-        from lit_llama_b200 import _lib as L
-        import ctypes as C
-        launches = L.lib().b2l_decode_step_launches(C.byref(model._decode.args))
-        line = {
-            "metric": "LLaMA-7B gptq.int4 decode tokens/sec", "value": aggregate_throughput(world, K, t_dev), "unit": "tokens/s", "n_gpus": world,
-            "steps": K, "warmup": warm, "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "LLaMA-7B gptq.int4 decode batch=1 ctx=2048 (random-init weights)", "prompt_tokens": PROMPT_T,
-                       "positions": f"{K} positions spread evenly over {lo}..{S_CTX - 1} (mean {mean_p:.0f})",
-                       "points": {**points, "unit": "tokens/s at fixed position"}, "sampling": f"top_k={TOP_K} temperature={TEMPERATURE}",
-                       "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
-                       "l2": "weights 3.31 GB per token >> 126 MB L2 (inputs larger than L2)"},
-            "clocks": clk,
-            "e2e": {"value": aggregate_throughput(world, Ke, t_e2e), "unit": "tokens/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 8, "steps": Ke},
-            "gpu_launches": (launches + 1) * K,  # b2l_decode_step's kernels + the fused sampling kernel, per token
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                         "kernel": q4_name, "launches_per_token": n_q4, "bytes_per_token_launches": W,
-                         "peak_source": which,
-                         "whole_token_bytes": bytes_per_token, "whole_token_achieved": bytes_per_token * K / t_dev / 1e9,
-                         "whole_token_frac": bytes_per_token * K / t_dev / 1e9 / peak},
-        }
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import tp_bench
+
+            tp = {"7B": tp_bench.run_tp("7B", 96, 8, dev, rank, world)}
+            if world == 8:
+                tp["65B"] = tp_bench.run_tp("65B", 64, 8, dev, rank, world)
+        except Exception as e:  # noqa: BLE001 -- reported in the line, the replicas numbers stand
+            tp = {"error": f"{type(e).__name__}: {e}"[:300]}
+        watchdog.cancel()
+
+    if rank == 0:
+        line = build_line(args, world, K, warm, t_dev, t_e2e, Ke, timed_pos, points, clk, t_q4, n_q4, q4_name, launches, lo)
+        if tp is not None:
+            line["tp"] = tp
         if not args.no_cpu_baseline and world == 1:
-            del model
+            model = None
             torch.cuda.empty_cache()
             cb = cpu_reference_tokens(n_tokens=1, budget_s=30.0, prompt_t=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # No orderly teardown: with peer-mapped (symmetric-memory) buffers alive, destroy_process_group / interpreter
+        # exit was measured to block on a 2-GPU box AFTER every rank had finished; the result line is out, nothing is
+        # left to flush, and a failed collective may have left peers waiting anyway.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

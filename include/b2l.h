@@ -247,6 +247,27 @@ int b2l_attention(void* qkv, void* k_cache, void* v_cache, const void* rope,
                   int T, int n_head, int head_size, int S, int block_size, int flags,
                   b2l_stream_t stream);
 
+/* ------------------------------------------------------------------------------
+ * Tensor-parallel decode (new capability: every reference script is Fabric(devices=1); the split dims are the ones
+ * scripts/convert_checkpoint.py:56-64 records).  One-shot all-reduce (sum, fp32 accumulation in rank order, one
+ * rounding) of a bf16 row of n elements over the GPUs of one node, through peer memory: every rank pushes
+ * {2 values, epoch} words into its slot of every peer's exchange buffer (NVLink stores) and polls its own buffer
+ * (csrc/tp_allreduce.cu).  `out` may alias `partial`.  All ranks must issue the same sequence of calls.
+ * peer_buf[r]: rank r's buffer of b2l_tp_buffer_bytes(world, max_elems) bytes as mapped into this process
+ * (peer_buf[rank] = the local one), zero-filled once before the first call; epoch: 16 local device words, status:
+ * one, zero-filled once.  status becomes 1 if a bounded wait timed out (the result is then undefined).
+ * ---------------------------------------------------------------------------- */
+typedef struct b2l_tp_comm {
+  void* peer_buf[8];
+  int rank, world;
+  int max_elems;
+  unsigned int* epoch;
+  int* status;
+} b2l_tp_comm;
+size_t b2l_tp_buffer_bytes(int world, int max_elems);
+int b2l_tp_allreduce(const b2l_tp_comm* comm, const void* partial, void* out, int n, int flags,
+                     b2l_stream_t stream);
+
 /* The roll branch of model.py:214-218 as a ring: if input_pos[T-1] >= S the ring start
  * advances by one slot (the oldest entry is dropped, exactly what torch.roll(-1) +
  * overwrite of slot S-1 does).  Call once per forward, before the layers. */

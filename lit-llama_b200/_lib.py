@@ -58,6 +58,10 @@ class DecodeArgs(C.Structure):
     ]
 
 
+class TPComm(C.Structure):
+    _fields_ = [("peer_buf", c_void_p * 8), ("rank", c_int), ("world", c_int), ("max_elems", c_int), ("epoch", c_void_p), ("status", c_void_p)]
+
+
 _SIGS = {
     "b2l_version": (c_int, []),
     "b2l_last_error": (C.c_char_p, []),
@@ -92,6 +96,8 @@ _SIGS = {
     "b2l_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "b2l_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b2l_tp_buffer_bytes": (c_size_t, [c_int, c_int]),
+    "b2l_tp_allreduce": (c_int, [C.POINTER(TPComm), c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "b2l_ring_advance": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "b2l_attention_nocache": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b2l_kv_unroll": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -22,6 +22,8 @@ The per-rank partial products are rounded to bf16 before the reduction (the kern
 dtype), so a TP result can differ from the single-GPU one by one bf16 ulp per reduction.
 """
 import ctypes as C
+import os
+import sys
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -116,7 +118,7 @@ class _TPBlock(nn.Module):
 
 class _TPDecodeState:
     """Batch-1 decode step of one rank as a fixed launch sequence over static buffers (captured once into a CUDA graph,
-    NCCL all-reduces included): the single-GPU path's fused kernels on the local shards --
+    all-reduces included: b2l_tp_allreduce over peer memory, or NCCL when that is unavailable): the single-GPU path's fused kernels on the local shards --
       [rms_1 + c_attn(local heads)] -> fused attention (local heads) -> [c_proj (K = local heads) (+ residual on rank 0)]
       -> all-reduce -> [rms_2 + c_fc1|c_fc2 (local columns) + SwiGLU] -> [mlp.c_proj (K = local columns) (+ residual on
       rank 0)] -> all-reduce; finally [ln_f + lm_head (local vocabulary rows)] -> all-gather.
@@ -186,6 +188,7 @@ class _TPDecodeState:
         self.ops.append(("gemv", lin(m.lm_head, self.x, self.logits_l, L.PRO_RMSNORM, bf16(m.transformer.ln_f.scale))))
         self.ops.append(("allgather",))
         self.m, self.S = m, S
+        self.comm = m.tp_comm(dev)
         self.wte = bf16(m.transformer.wte.weight)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.calls = 0
@@ -206,7 +209,10 @@ class _TPDecodeState:
                                           m._ring.data_ptr(), self.att.data_ptr(), self.work.data_ptr(), 1, 1, m.nh_l, m.hs, self.S,
                                           cfg.block_size, L.F_PDL, sp), "b2l_attention")
             elif op[0] == "allreduce":
-                if m.world > 1:
+                if self.comm is not None:   # one-shot sum over peer memory (NVLink), in place, inside the PDL chain
+                    L.check(lib.b2l_tp_allreduce(C.byref(self.comm), op[1].data_ptr(), op[1].data_ptr(), op[1].numel(), L.F_PDL, sp),
+                            "b2l_tp_allreduce")
+                elif m.world > 1:
                     dist.all_reduce(op[1], op=dist.ReduceOp.SUM, group=m.group)
             else:
                 if m.world > 1:
@@ -242,12 +248,55 @@ class TPLLaMA(nn.Module):
         self.graph_after = 2
         #: fused per-rank decode step (batch 1, head_size 128, K % 64 == 0); False: module by module
         self.fast_decode = True
+        self._comm, self._comm_keep, self._comm_tried = None, None, False
 
     def reset_cache(self) -> None:
         self.kv_caches.clear()
         self._decode = None
         if self._ring is not None:
             self._ring.zero_()
+
+    def tp_comm(self, dev: torch.device) -> Optional["L.TPComm"]:
+        """The peer-memory exchange of b2l_tp_allreduce (csrc/tp_allreduce.cu), created once per model (a collective
+        call: every rank must get here).  Buffers come from torch's symmetric memory -- allocation + peer mapping
+        only, the all-reduce itself is this library's kernel.  None when world == 1, when B2L_TP_ALLREDUCE=nccl, or
+        when the peer mapping is unavailable (said once on stderr): the step then uses NCCL all-reduces."""
+        if self._comm_tried:
+            return self._comm
+        self._comm_tried = True
+        if self.world == 1 or os.environ.get("B2L_TP_ALLREDUCE", "ll") == "nccl":
+            return None
+        lib = L.lib()
+        C_ = self.config.n_embd
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            nbytes = lib.b2l_tp_buffer_bytes(self.world, C_)
+            buf = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            assert len(ptrs) == self.world
+        except Exception as e:  # noqa: BLE001 -- any failure of the optional peer mapping selects the NCCL path, loudly
+            print(f"[lit_llama_b200.tp] peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduces", file=sys.stderr, flush=True)
+            return None
+        words = torch.zeros(32, dtype=torch.int32, device=dev)   # [0..15] epochs, [16] status
+        comm = L.TPComm()
+        for r in range(self.world):
+            comm.peer_buf[r] = ptrs[r]
+        comm.rank, comm.world, comm.max_elems = self.rank, self.world, C_
+        comm.epoch, comm.status = words.data_ptr(), words.data_ptr() + 64
+        self._comm, self._comm_keep = comm, (buf, hdl, words)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)   # every rank's buffer is zeroed before anyone pushes
+        return comm
+
+    def tp_check(self) -> None:
+        """Raises if a bounded wait inside b2l_tp_allreduce ever timed out (a peer stopped issuing its calls)."""
+        if self._comm is not None:
+            torch.cuda.synchronize()
+            if int(self._comm_keep[2][16]) != 0:
+                raise RuntimeError("b2l_tp_allreduce: a wait for a peer's partial row timed out; results are invalid")
 
     def _all_reduce(self, t: torch.Tensor) -> torch.Tensor:
         if self.world > 1:

@@ -100,9 +100,12 @@ def run_tp(name, steps, warmup, dev, rank, world, group=None, pos0=16):
     mean_p = sum(timed) / steps
     bytes_rank = w_rank + kv_rank_per_pos * (mean_p + 2)
     st = model._decode
+    model.tp_check()
+    ll = st is not None and getattr(st, "comm", None) is not None
     res = {"model": f"LLaMA-{name} gptq.int4", "tp": world, "tokens_per_s": steps / t, "ms_per_token": t / steps * 1e3, "steps": steps,
            "positions": f"{steps} positions spread evenly over {pos0}..{S - 1}", "graph": bool(st is not None and st.graph is not None),
-           "allreduces_per_token": 2 * L_, "collective": "NCCL all-reduce (bf16 sum) inside the captured graph + all-gather of the logits",
+           "allreduces_per_token": 2 * L_, "collective": ("b2l_tp_allreduce: one-shot sum over peer memory (NVLink stores of {2 x bf16, epoch} words, fp32 sum in rank order) inside "
+                          "the captured graph" if ll else "NCCL all-reduce (bf16 sum) inside the captured graph") + "; NCCL all-gather of the logits",
            "per_rank_weight_bytes": w_rank, "per_rank_hbm_frac": bytes_rank / (t / steps) / 1e9 / peak}
     del model
     torch.cuda.empty_cache()
@@ -126,8 +129,9 @@ def main():
     res = run_tp(args.model, args.steps, args.warmup, dev, rank, world)
     if rank == 0:
         print(json.dumps(res), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if world > 1:   # see bench.py: teardown with peer-mapped buffers alive can block; everything is printed
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -43,6 +43,7 @@ def parity(cfg, rank, world, dev, S, steps, label):
         for i, t in enumerate(toks):
             got.append(tp(torch.tensor([[t]], device=dev), S, torch.tensor([7 + i], device=dev)))
     fast = tp._decode is not None and tp._decode.graph is not None
+    tp.tp_check()
     worst = 0.0
     if rank == 0:
         prev = torch.get_default_dtype()
@@ -59,7 +60,7 @@ def parity(cfg, rank, world, dev, S, steps, label):
             rel = float((a.float() - b.float()).norm() / b.float().norm())
             worst = max(worst, rel)
         print(f"[tp={world}] {label}: {len(got)} steps, worst normwise error vs the single-GPU model {worst:.3e} "
-              f"(fused graph-replayed rank step: {fast}) {'OK' if worst < 1e-2 else 'MISMATCH'}", flush=True)
+              f"(fused graph-replayed rank step: {fast}, peer-memory all-reduce: {tp._comm is not None}) {'OK' if worst < 1e-2 else 'MISMATCH'}", flush=True)
     w = torch.tensor([worst], device=dev)
     dist.broadcast(w, 0)
     dist.barrier()
@@ -77,9 +78,8 @@ def main():
     nh = 2 * world
     e2 = parity(dict(block_size=128, vocab_size=32 * world * 5, n_layer=3, n_head=nh, n_embd=128 * nh), rank, world, dev, 64, 6,
                 f"{nh}-head model (head_size 128, fused rank step)")
-    dist.destroy_process_group()
-    if max(e1, e2) >= 1e-2:
-        sys.exit(1)
+    sys.stdout.flush()
+    os._exit(1 if max(e1, e2) >= 1e-2 else 0)   # no teardown: it can block with peer-mapped buffers alive (see bench.py)
 
 
 if __name__ == "__main__":
