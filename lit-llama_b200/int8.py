@@ -13,6 +13,7 @@ arithmetic follows the published algorithm (parity with the reference is unpinne
 import torch
 
 from . import _lib as L
+from .quantization import weights_changed
 
 
 def quantize_rows_int8(weight: torch.Tensor):
@@ -48,6 +49,7 @@ class Linear8bitLt(torch.nn.Module):
         setattr(self.weight, "CB", cb)
         setattr(self.weight, "SCB", scb)
         self._tiled = None
+        weights_changed()
 
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
@@ -57,6 +59,7 @@ class Linear8bitLt(torch.nn.Module):
             self.weight.SCB = scb.to(self.weight.device)
             self.weight.CB = self.weight.data
         self._tiled = None
+        weights_changed()
         return out
 
     def _load_from_state_dict(self, local_state_dict, prefix, *args, **kwargs):
@@ -73,6 +76,7 @@ class Linear8bitLt(torch.nn.Module):
                 self.weight.CB = self.weight.data
                 self.weight.SCB = scb.to(self.weight.device).float().contiguous()
                 self._tiled = None
+                weights_changed()
             else:
                 self._quantize_weight(w)
         local_state_dict.pop(prefix + "SCB", None)

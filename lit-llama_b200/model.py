@@ -22,6 +22,7 @@ import torch.nn as nn
 from typing_extensions import Self
 
 from . import _lib as L
+from .quantization import WEIGHTS_GENERATION
 from .utils import find_multiple
 
 MaskCache = torch.Tensor
@@ -235,6 +236,7 @@ class _DecodeState:
         hs = C_ // nh
         bf = dict(device=device, dtype=torch.bfloat16)
         self.B, self.S = B, S
+        self.generation = WEIGHTS_GENERATION[0]   # raw weight pointers below are valid for this generation only
         self.idx = torch.zeros(B, dtype=idx_dtype, device=device)
         self.pos = torch.zeros(1, dtype=torch.int64, device=device)
         self.x = torch.empty((B, C_), **bf)
@@ -477,7 +479,13 @@ class LLaMA(nn.Module):
         st = None
         if input_pos is not None and T == 1 and B <= 16 and idx.dtype in (torch.int32, torch.int64):
             st = self._decode
-            if st is None or st.B != B or st.S != max_seq_length or st.idx.dtype != idx.dtype:
+            if st is not None and st.generation != WEIGHTS_GENERATION[0]:
+                # a linear was reloaded, repacked or moved since the argument block / graph was built: everything that
+                # bakes weight pointers is stale (fc1|fc2 interleave, eligibility, module graph included)
+                st = self._decode = None
+                self._module_graph, self._fast_ok = None, None
+                self._fc12_cache.clear()
+            if st is None or st.B != B or st.S != max_seq_length or st.idx.dtype != idx.dtype or st.idx.device != idx.device:
                 if self._fast_ok is None:
                     self._fast_ok = self._fast_decode_ok()
                 st = self._decode = _DecodeState(self, B, max_seq_length, idx.device, idx.dtype) if self._fast_ok else None
@@ -500,7 +508,7 @@ class LLaMA(nn.Module):
         # ---- single-token decode with any other Linear kind (llm.int8, gptq.int8, grouped scales, dense):
         #      the module-by-module launch sequence, replayed as a CUDA graph once warm
         if input_pos is not None and T == 1 and self.graph_after and idx.dtype in (torch.int32, torch.int64):
-            key = (B, max_seq_length, idx.dtype)
+            key = (B, max_seq_length, idx.dtype, idx.device, WEIGHTS_GENERATION[0])   # the graph bakes weight pointers too
             mg = self._module_graph
             if mg is None or mg["key"] != key:
                 mg = self._module_graph = dict(key=key, calls=0, graph=None, idx=torch.zeros((B, 1), dtype=idx.dtype, device=idx.device),

@@ -21,6 +21,15 @@ BATCH_GEMV = os.environ.get("B2L_BATCH_GEMV", "1") != "0"
 _BATCH_WS = {}
 _BATCH_WS_OLD = []
 
+#: bumped whenever a quantized linear's storage may have changed (load_state_dict, pack_weight, .to()/_apply): the
+#: decode state of LLaMA bakes raw pointers to the re-tiled weights into a C argument block / CUDA graph and rebuilds
+#: when this differs from the value it was built at
+WEIGHTS_GENERATION = [0]
+
+
+def weights_changed() -> None:
+    WEIGHTS_GENERATION[0] += 1
+
 
 def batch_workspace(device, K: int) -> torch.Tensor:
     """Scratch of b2l_q4_gemv_batch (activation fragments), one per device, grown to the largest K seen.
@@ -83,7 +92,18 @@ class ColBlockQuantizedLinear(torch.nn.Module):
         self.quant_weight.zero_()
         for nr in range(self.entries_per_byte):
             self.quant_weight += weight[:, nr :: self.entries_per_byte] << (nr * self.bits)
-        self._tiled = None
+        self._tiled = self._tiled_mma = self._tiled_i8 = None
+        weights_changed()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)   # copies in place: pointers stay, contents (and _version) change
+        weights_changed()
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self._tiled = self._tiled_mma = self._tiled_i8 = None   # another device / dtype: the tilings are rebuilt on demand
+        weights_changed()
+        return out
 
     # ------------------------------------------------------------------ device paths
     def _check_layout(self):

@@ -135,6 +135,31 @@ def test_fast_path_equals_module_path(dev):
     torch.testing.assert_close(fast.float(), slow.float(), rtol=RTOL, atol=ATOL)
 
 
+def test_reloading_weights_invalidates_the_baked_decode_state(dev):
+    """load_state_dict after decode steps (argument block and CUDA graph already built on the old tilings): the next
+    step must use the new weights -- the decode state is rebuilt, not replayed on stale pointers."""
+    from gpu_util import build_tiny
+
+    model, _, _ = build_tiny(dev, CFG, seed=1234)
+    fresh, _, sd2 = build_tiny(dev, CFG, seed=4321)
+    prompt = torch.tensor([[3, 17, 40, 41, 2, 77, 5]], device=dev)
+
+    def run(m):
+        m.reset_cache()
+        out = [m(prompt, 16, torch.arange(7, device=dev))]
+        for i, t in enumerate([9, 11, 60, 2]):   # graph replay from the third step
+            out.append(m(torch.tensor([[t]], device=dev), 16, torch.tensor([7 + i], device=dev)).clone())
+        return out
+
+    with torch.no_grad():
+        old = run(model)
+        model.load_state_dict(sd2)
+        new, want = run(model), run(fresh)
+    assert not torch.equal(old[-1], new[-1])
+    for a, b in zip(new, want):
+        assert torch.equal(a, b)
+
+
 def test_7b_shaped_block_vs_oracle(dev):
     """One Block + lm_head at the BASELINE 7B widths (n_embd 4096, 32 heads of 128, n_hidden
     11008, vocab 32000): prefill 5 tokens (tcgen05 kernel, prefill attention) then 3 decode
@@ -161,12 +186,49 @@ def test_7b_shaped_block_vs_oracle(dev):
         scale = b.abs().max()
         # every module output is rounded to bf16 (2^-9 normwise each) on 4096..11008-wide vectors and
         # single-ulp flips propagate through the next RMSNorm/linear: a percent normwise end to end
-        assert (a - b).norm() / b.norm() < 2e-2, float((a - b).norm() / b.norm())
+        ours = float((a - b).norm() / b.norm())
+        # the measured anchor of that bound: the REFERENCE's own bf16 CPU arithmetic (dense branch, bf16-rounded
+        # weights) sits this far from the same exact-arithmetic result; ours must not be farther than it is
+        # (plus the bf16 rounding of the logits themselves)
+        ref = float((c - b).norm() / b.norm())
+        assert ours < 2e-2, (ours, ref)
+        assert ours <= 1.25 * ref + 2.0 ** -8, (ours, ref)
         assert (a - b).abs().max() < 0.05 * scale
         assert (a - c).norm() / c.norm() < 3e-2
     k, v = model.kv_caches[0]
     torch.testing.assert_close(k[:, :, :8].float().cpu(), exact.kv[0][0].float(), rtol=2 ** -6, atol=2e-2)
     torch.testing.assert_close(v[:, :, :8].float().cpu(), exact.kv[0][1].float(), rtol=2 ** -6, atol=2e-2)
+
+
+def test_13b_width_batch8_prefill_and_decode_vs_oracle(dev):
+    """BASELINE.json configs[3] in small: two Blocks at the LLaMA-13B widths (n_embd 5120, 40 heads of 128, n_hidden
+    13824), batch 8: prefill 32 tokens per sequence (tcgen05 GEMM at M = 256, tensor-core prefill attention), then 4
+    decode steps (2..8-row mma.sync kernel, fused attention, CUDA graph from the third step), every logits tensor and
+    the KV cache against the oracle in exact arithmetic."""
+    from gpu_util import build_tiny
+
+    cfg = dict(block_size=64, vocab_size=512, n_layer=2, n_head=40, n_embd=5120)
+    model, exact, _ = build_tiny(dev, cfg, seed=3, exact_linears=True)
+    g = torch.Generator().manual_seed(0)
+    B, T, S = 8, 32, 40
+    prompt = torch.randint(0, 512, (B, T), generator=g)
+    steps = [torch.randint(0, 512, (B, 1), generator=g) for _ in range(4)]
+    with torch.no_grad():
+        got = [model(prompt.to(dev), S, torch.arange(T, device=dev))]
+        want = [exact.forward(prompt, S, torch.arange(T))]
+        for i, t in enumerate(steps):
+            got.append(model(t.to(dev), S, torch.tensor([T + i], device=dev)))
+            want.append(exact.forward(t, S, torch.tensor([T + i])))
+    for a, b in zip(got, want):
+        a, b = a.float().cpu(), b.float()
+        assert a.shape == b.shape
+        assert (a - b).norm() / b.norm() < 2e-2, float((a - b).norm() / b.norm())
+        for r in range(B):   # every sequence on its own: a row mix-up cannot hide in the batch norm
+            assert (a[r] - b[r]).norm() / b[r].norm() < 3e-2, (r, float((a[r] - b[r]).norm() / b[r].norm()))
+    for li in range(2):
+        k, v = model.kv_caches[li]
+        torch.testing.assert_close(k[:, :, :T + 4].float().cpu(), exact.kv[li][0][:, :, :T + 4].float(), rtol=2 ** -6, atol=3e-2)
+        torch.testing.assert_close(v[:, :, :T + 4].float().cpu(), exact.kv[li][1][:, :, :T + 4].float(), rtol=2 ** -6, atol=3e-2)
 
 
 @pytest.mark.parametrize("S,cases", [
