@@ -4,6 +4,7 @@
 RNG stream of `torch.multinomial` is the reference's); the model call inside it is one
 CUDA-graph replay per token.  `main()` mirrors the reference CLI with argparse
 (jsonargparse and lightning are not dependencies of this path)."""
+import os
 import sys
 import time
 from pathlib import Path
@@ -124,6 +125,11 @@ def main(
     model.load_state_dict(checkpoint)
     print(f"Time to load model: {time.time() - t0:.02f} seconds.", file=sys.stderr)
     model.eval()
+    if quantize == "gptq.int4" and os.environ.get("B2L_COMPACT", "1") != "0":
+        try:
+            model.compact()   # one resident copy of the weights (the reference-layout buffers come back on state_dict())
+        except RuntimeError:  # a layer the fused decode step cannot run (grouped scales, odd widths): keep everything
+            pass
 
     sp = SentencePieceProcessor(model_file=str(tokenizer_path))
     encoded = torch.tensor([sp.bos_id()] + sp.encode(prompt), dtype=torch.int, device=device)

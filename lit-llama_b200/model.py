@@ -259,6 +259,7 @@ class _DecodeState:
 
         def q4(lin: ColBlockQuantizedLinear) -> L.Q4Weight:
             t = (lin.tiled_i8() if B == 1 else lin.tiled_mma()) if gemv else lin.tiled()
+            self.keep.append(t)   # a compacted layer hands out transient tilings: this state owns the ones it points at
             return L.Q4Weight(None if gemv else t.data_ptr(), t.data_ptr() if gemv else None, lin.scales.data_ptr(),
                               lin.zeros.data_ptr(), lin.out_features, lin.in_features)
 
@@ -385,9 +386,11 @@ class LLaMA(nn.Module):
         tile holds silu's argument and its multiplier and SwiGLU runs in the epilogue."""
         mlp = self.transformer.h[i].mlp
         gemv = kind != "tc"
-        key = (kind, mlp.c_fc1.quant_weight.data_ptr(), mlp.c_fc1.quant_weight._version,
-               mlp.c_fc2.quant_weight.data_ptr(), mlp.c_fc2.quant_weight._version)
         hit = self._fc12_cache.get((i, kind))
+        if hit is not None and getattr(mlp.c_fc1, "_released", False):
+            return hit[1]     # compacted: this copy IS the layer's weights (compact())
+        q1, q2 = mlp.c_fc1.reference_quant_weight(), mlp.c_fc2.reference_quant_weight()
+        key = (kind, q1.data_ptr(), q1._version, q2.data_ptr(), q2._version)
         if hit is not None and hit[0] == key:
             return hit[1]
         nh, K = mlp.c_fc1.out_features, mlp.c_fc1.in_features
@@ -397,7 +400,7 @@ class LLaMA(nn.Module):
         def inter(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:  # rows (dim 0) of a, b -> [t][g of a | g of b]
             return torch.stack((a.reshape(nh // g, g, *a.shape[1:]), b.reshape(nh // g, g, *b.shape[1:])), dim=1).reshape(2 * nh, *a.shape[1:])
 
-        qw = inter(mlp.c_fc1.quant_weight, mlp.c_fc2.quant_weight).t().contiguous().t()  # reference layout (1, 2nh)
+        qw = inter(q1, q2).t().contiguous().t()  # reference layout (1, 2nh)
         scales = inter(mlp.c_fc1.scales, mlp.c_fc2.scales).contiguous()
         zeros = inter(mlp.c_fc1.zeros, mlp.c_fc2.zeros).contiguous()
         lib = L.lib()
@@ -413,6 +416,48 @@ class LLaMA(nn.Module):
         val = (tiled, scales, zeros)
         self._fc12_cache[(i, kind)] = (key, val)
         return val
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        # the interleaved fc1|fc2 copies are plain tensors of this module: they move with it (a compacted model has no other)
+        self._fc12_cache = {k: (key, tuple(fn(t) for t in val)) for k, (key, val) in self._fc12_cache.items()}
+        self._decode, self._module_graph, self._fast_ok = None, None, None
+        return out
+
+    def _fc_from_fc12(self, i: int, which: int) -> torch.Tensor:
+        """c_fc1 (which = 0) or c_fc2 (1) of layer i in the reference layout, rebuilt from the interleaved batch-1
+        tiling (compacted models keep only that copy): untile (a nibble permutation) and take every other 8 rows."""
+        tiled, _, _ = self._fc12_cache[(i, "i8")][1]
+        mlp = self.transformer.h[i].mlp
+        nh, K = mlp.c_fc1.out_features, mlp.c_fc1.in_features
+        both = torch.empty((K // 2, 2 * nh), dtype=torch.uint8, device=tiled.device).t()
+        L.check(L.lib().b2l_q4_untile_i8(tiled.data_ptr(), both.data_ptr(), 2 * nh, K, L.stream_ptr()), "b2l_q4_untile_i8")
+        return both.contiguous().reshape(nh // 8, 2, 8, K // 2)[:, which].reshape(nh, K // 2).t().contiguous().t()
+
+    def compact(self) -> "LLaMA":
+        """Keep ONE resident copy of every gptq.int4 weight: the batch-1 decode tiling (c_fc1 / c_fc2: the interleaved
+        fc1|fc2 tiling).  The reference-layout buffers and the per-kernel duplicates are freed; `state_dict()`, prefill
+        and batched decode rebuild what they need transiently from that copy (bit-exact permutations).  7B: 3.3 GB of
+        weights + 0.26 GB embedding + KV cache instead of 2-3 copies (the reference's gptq.int4 figure is "~5 GB",
+        howto/inference.md:37).  Returns self."""
+        import functools
+
+        if self._fast_ok is None:
+            self._fast_ok = self._fast_decode_ok()
+        if not self._fast_ok:
+            raise RuntimeError("compact() needs a gptq.int4 model the fused batch-1 decode step can run")
+        for i, blk in enumerate(self.transformer.h):
+            self._fc12(i, "i8")
+            for kind in ("mma", "tc"):
+                self._fc12_cache.pop((i, kind), None)
+            for lin in (blk.attn.c_attn, blk.attn.c_proj, blk.mlp.c_proj):
+                lin.release_reference_layout()
+            blk.mlp.c_fc1.release_reference_layout(source=functools.partial(self._fc_from_fc12, i, 0))
+            blk.mlp.c_fc2.release_reference_layout(source=functools.partial(self._fc_from_fc12, i, 1))
+        self.lm_head.release_reference_layout()
+        self._decode, self._module_graph = None, None   # rebuilt on the next step (B > 1 states hold their transient tilings)
+        torch.cuda.empty_cache()
+        return self
 
     def _fast_decode_ok(self) -> bool:
         from .quantization import ColBlockQuantizedLinear

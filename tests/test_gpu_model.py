@@ -160,6 +160,56 @@ def test_reloading_weights_invalidates_the_baked_decode_state(dev):
         assert torch.equal(a, b)
 
 
+def test_compact_keeps_one_copy_and_changes_nothing(dev):
+    """LLaMA.compact(): the reference-layout buffers and duplicate tilings are freed (one resident copy = the batch-1
+    decode tiling), prefill / batch-1 / batch-2 decode results stay bit-identical, state_dict() still yields the
+    reference's tensors bit for bit (rebuilt from the tiling), and load_state_dict() brings the buffers back."""
+    from gpu_util import build_tiny
+
+    model, _, sd = build_tiny(dev, CFG, seed=77)
+    twin, _, _ = build_tiny(dev, CFG, seed=77)
+    prompt = torch.tensor([[3, 17, 40, 41, 2, 77, 5]], device=dev)
+
+    def run(m, B=1):
+        m.reset_cache()
+        out = [m(prompt.repeat(B, 1), 16, torch.arange(7, device=dev))]
+        for i, t in enumerate([9, 11, 60, 2]):
+            out.append(m(torch.full((B, 1), t, device=dev), 16, torch.tensor([7 + i], device=dev)).clone())
+        return out
+
+    with torch.no_grad():
+        before = run(model)
+        before_sd = {k: v.clone() for k, v in model.state_dict().items()}
+        torch.cuda.synchronize()
+        model.reset_cache()
+        m0 = torch.cuda.memory_allocated()
+        model.compact()
+        torch.cuda.synchronize()
+        m1 = torch.cuda.memory_allocated()
+        after = run(model)
+        after2, want2 = run(model, B=2), run(twin, B=2)
+    assert m1 < m0, (m0, m1)
+    for a, b in zip(before, after):
+        assert torch.equal(a, b)
+    for a, b in zip(after2, want2):
+        assert torch.equal(a, b)
+    lin = model.transformer.h[0].attn.c_attn
+    assert lin.quant_weight.numel() == 0 and model.transformer.h[1].mlp.c_fc1._tiled_i8 is None
+    got_sd = model.state_dict()
+    assert got_sd.keys() == before_sd.keys()
+    for k, v in before_sd.items():
+        assert torch.equal(got_sd[k], v), k
+        if k.endswith("quant_weight"):
+            assert got_sd[k].stride() == v.stride(), k
+    # a new checkpoint after compaction: buffers come back, results follow the new weights
+    other, _, sd2 = build_tiny(dev, CFG, seed=78)
+    with torch.no_grad():
+        model.load_state_dict(sd2)
+        for a, b in zip(run(model), run(other)):
+            assert torch.equal(a, b)
+    assert lin.quant_weight.numel() > 0
+
+
 def test_7b_shaped_block_vs_oracle(dev):
     """One Block + lm_head at the BASELINE 7B widths (n_embd 4096, 32 heads of 128, n_hidden
     11008, vocab 32000): prefill 5 tokens (tcgen05 kernel, prefill attention) then 3 decode
