@@ -406,6 +406,10 @@ def main():
     K = args.steps
 
     model = build_synthetic_model(MODEL, dev, seed=1234)   # every replica holds the same weights, decodes its own stream
+    compacted = False
+    if os.environ.get("B2L_COMPACT", "1") != "0":
+        model.compact()     # one resident copy of the weights, as generate.py runs the model (lit_llama_b200/model.py)
+        compacted = True
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     prompt = torch.randint(0, 32000, (PROMPT_T,), device=dev, dtype=torch.int32, generator=gen)
     lo, span = PROMPT_T, S_CTX - PROMPT_T
@@ -481,6 +485,8 @@ def main():
             points[f"p{q}"] = round(24 / (p0.elapsed_time(p1) * 1e-3), 1)
 
         t_q4, n_q4, q4_name = time_q4_launches(model, dev)
+        resident = {"allocated_gb": round(torch.cuda.memory_allocated(dev) / 1e9, 3), "compacted": compacted,
+                    "what": "torch.cuda.memory_allocated after the timed loops: weights (one copy when compacted), embedding, KV cache S=2048, activations"}
 
     t_dev, t_e2e = reduce_max([t_dev, t_e2e], dev)
 
@@ -521,6 +527,7 @@ def main():
 
     if rank == 0:
         line = build_line(args, world, K, warm, t_dev, t_e2e, Ke, timed_pos, points, clk, t_q4, n_q4, q4_name, launches, lo)
+        line["config"]["resident_memory"] = resident
         if tp is not None:
             line["tp"] = tp
         if not args.no_cpu_baseline and world == 1:

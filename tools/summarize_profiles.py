@@ -15,7 +15,8 @@ P = os.path.join(ROOT, "profiles")
 WANT = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
         "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
@@ -91,6 +92,7 @@ if __name__ == "__main__":
         launch_list(tag, os.path.join(G, "launches_r1.csv"), "one eager decode step of LLaMA-7B gptq.int4 (tools/prof_step.py), every launch")
     for rep, name, title in [("prof_gemv.ncu-rep", "q4_gemv_kernel", "q4_gemv_kernel: c_attn, attn.c_proj, fc1|fc2, mlp.c_proj of layer 0 and c_attn of layer 1 (7B, batch 1)"),
                              ("prof_attn.ncu-rep", "attn_decode_fused_kernel", "attn_decode_fused_kernel (7B, batch 1)"),
+                             ("prof_gemm.ncu-rep", "q4_gemm_kernel", "q4_gemm_kernel: tcgen05 prefill GEMM, 13B c_attn shape (N 15360, K 5120) at M = 4096 (tools/diag.py bench_gemm)"),
                              ("prof_q4.ncu-rep", "q4_linear_tc_kernel", "q4_linear_tc_kernel (tcgen05 path; first revision, 4 convert warps)")]:
         if os.path.exists(os.path.join(G, rep)):
             full(tag, rep, name, title)
