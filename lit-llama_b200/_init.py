@@ -10,12 +10,11 @@ from .model import LLaMA, LLaMAConfig, Block, CausalSelfAttention, MLP, RMSNorm,
 from .quantization import ColBlockQuantizedLinear
 from .int8 import Linear8bitLt
 from .utils import find_multiple, llama_model_lookup
-from .gptq import GPTQQuantizer
 from .generate import generate, sample_probs, sample_token
 from .patch import patch_reference
 from .tp import TPLLaMA, shard_state_dict
 
 __all__ = [
     "LLaMA", "LLaMAConfig", "Block", "CausalSelfAttention", "MLP", "RMSNorm", "build_rope_cache", "apply_rope",
-    "ColBlockQuantizedLinear", "Linear8bitLt", "find_multiple", "llama_model_lookup", "generate", "sample_probs", "sample_token", "patch_reference", "TPLLaMA", "shard_state_dict", "GPTQQuantizer",
+    "ColBlockQuantizedLinear", "Linear8bitLt", "find_multiple", "llama_model_lookup", "generate", "sample_probs", "sample_token", "patch_reference", "TPLLaMA", "shard_state_dict",
 ]

@@ -448,44 +448,38 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   if (threadIdx.x == 0) tl_max(tl, 2);
   __syncwarp();
   if (threadIdx.x == 0) tl_max(tl, 3);
-  // merge the 4 key groups of the warp (lanes with the same `sub` hold the same dims)
+  // ---- merge the 32 (warp, key group) partials of the CTA through shared memory: the K / V ring is idle now (every
+  // requested sub-tile has been consumed behind a __syncthreads), so its first 16 KB hold the partial rows.  One warp
+  // turns the 32 running maxima into weights, 128 threads add.  (Round 1 merged the key groups with 36 shuffles per
+  // warp first: 0.8-1.3 us of a 4-8 us kernel, tools/diag.py timeline.)
+  float* part = reinterpret_cast<float*>(fsm);                 // [32][HS]
+  float* pm = part + 32 * HS;                                  // [32] running max, [32] sum, [32] weight, M, Ls
+  float* pl = pm + 32, *pw = pl + 32;
+  {
+    const int g = warp * 4 + grp;
+    float4* dst = reinterpret_cast<float4*>(part + g * HS + d0);
 #pragma unroll
-  for (int off = 8; off <= 16; off <<= 1) {
-    const float mo = __shfl_xor_sync(0xffffffffu, m, off);
-    const float lo = __shfl_xor_sync(0xffffffffu, l, off);
-    const float mn = fmaxf(m, mo);
-    const float ca = (m == -INFINITY) ? 0.f : __expf(m - mn);
-    const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
-    l = l * ca + lo * cb;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float ao = __shfl_xor_sync(0xffffffffu, acc[i], off);
-      acc[i] = acc[i] * ca + ao * cb;
-    }
-    m = mn;
-  }
-  // merge the warps through shared memory
-  if (lane == 0) { sm_m[warp] = m; sm_l[warp] = l; }
-  if (grp == 0) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) sm_acc[warp * HS + d0 + i] = acc[i];
+    for (int i = 0; i < 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    if (sub == 0) { pm[g] = m; pl[g] = l; }
   }
   __syncthreads();
-  float M = -INFINITY;
-#pragma unroll
-  for (int w = 0; w < FD_WARPS; ++w) M = fmaxf(M, sm_m[w]);
-  float wgt[FD_WARPS], Ls = 0.f;
-#pragma unroll
-  for (int w = 0; w < FD_WARPS; ++w) {
-    wgt[w] = (sm_m[w] == -INFINITY) ? 0.f : __expf(sm_m[w] - M);
-    Ls += sm_l[w] * wgt[w];
+  if (warp == 0) {
+    const float mi = pm[lane];
+    const float Mx = warp_max(mi);
+    const float wi = (mi == -INFINITY) ? 0.f : __expf(mi - Mx);
+    const float Lx = warp_sum(pl[lane] * wi);
+    pw[lane] = wi;
+    if (lane == 0) { pw[32] = Mx; pw[33] = Lx; }
   }
-  const int d = threadIdx.x & (HS - 1);  // threads >= HS duplicate the arithmetic and do not store
+  __syncthreads();
+  const float M = pw[32], Ls = pw[33];
+  const int d = threadIdx.x & (HS - 1);
   const bool writer = threadIdx.x < HS;
   float a = 0.f;
-#pragma unroll
-  for (int w = 0; w < FD_WARPS; ++w) a += sm_acc[w * HS + d] * wgt[w];
-
+  if (writer) {
+#pragma unroll 8
+    for (int g = 0; g < 32; ++g) a = fmaf(part[g * HS + d], pw[g], a);
+  }
   stamp();
   if (n_active == 1) {  // nothing to merge
     if (writer) y[(size_t)b * C + h * HS + d] = f2bf(a / Ls);

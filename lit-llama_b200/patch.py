@@ -10,7 +10,7 @@ same trick its own lora() context uses, lit_llama/lora.py:472-476).  After
 the reference's own `generate.py` (`main()`, `--quantize gptq.int4`) builds B200
 modules: `lit_llama.LLaMA`, `lit_llama.model.{LLaMA,Block,CausalSelfAttention,MLP,
 RMSNorm,apply_rope,build_rope_cache}`, `lit_llama.quantization.{ColBlockQuantizedLinear,
-Linear8bitLt,GPTQQuantizer}` and `lit_llama.utils.{quantization,EmptyInitOnDevice,lazy_load}`
+Linear8bitLt}` and `lit_llama.utils.{quantization,EmptyInitOnDevice,lazy_load}`
 all point at this package.
 """
 import sys
@@ -43,10 +43,9 @@ def patch_reference(lit_llama_module=None):
     ref_quant.Linear8bitLt = i8.Linear8bitLt
     saved[("quant", "qlinear_4bit_weight")] = getattr(ref_quant, "qlinear_4bit_weight", None)
     ref_quant.qlinear_4bit_weight = q.qlinear_4bit_weight
-    from . import gptq as gq
-
-    saved[("quant", "GPTQQuantizer")] = getattr(ref_quant, "GPTQQuantizer", None)
-    ref_quant.GPTQQuantizer = gq.GPTQQuantizer            # quantize/gptq.py:20 then converts into B200 modules
+    # The offline converter stays the reference's own (quantize/gptq.py + quantization.GPTQQuantizer, host-side torch,
+    # out of the decode path): it builds `ColBlockQuantizedLinear` through the name patched above and calls
+    # pack_weight(), so it converts straight into B200 modules.
     for name in ("EmptyInitOnDevice", "lazy_load"):
         saved[("utils", name)] = getattr(ref_utils, name, None)
         setattr(ref_utils, name, getattr(u, name))

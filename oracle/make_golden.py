@@ -164,43 +164,11 @@ def golden_dense_model():
     torch.save(dict(cfg=cfg, seed=3, prompt=prompt, gen=y), os.path.join(OUT, "tiny_dense_f32.pt"))
 
 
-GPTQ_CASES = [  # (out, in, bits, groupsize, actorder, blocksize, calibration batches (B, T), dead input features)
-    (24, 64, 4, -1, True, 128, [(2, 5), (1, 7), (3, 2)], []),
-    (16, 256, 4, -1, False, 128, [(2, 9), (2, 4)], []),          # two column blocks (grouped grids crash in the reference, quantization.py:578)
-    (8, 128, 8, -1, True, 32, [(4, 3)], [5, 77]),                 # int8, small blocks, two never-excited features
-    (32, 160, 4, -1, False, 128, [(1, 200)], []),                 # more tokens than features, two blocks
-]
-
-
-def golden_gptq():
-    """GPTQQuantizer end to end (hook -> Hessian -> quantize -> packed module) on small layers, CPU fp32."""
-    cases = []
-    for ci, (out_f, in_f, bits, gs, act, bs, batches, dead) in enumerate(GPTQ_CASES):
-        g = torch.Generator().manual_seed(100 + ci)
-        w = torch.randn(out_f, in_f, generator=g) * 0.05
-        xs = []
-        for (b, t) in batches:
-            x = torch.randn(b, t, in_f, generator=g)
-            x[..., dead] = 0
-            xs.append(x)
-        lin = torch.nn.Linear(in_f, out_f, bias=False)
-        lin.weight.data.copy_(w)
-        gq = GPTQQuantizer(lin, bits=bits, groupsize=gs, actorder=act, blocksize=bs)
-        for x in xs:
-            gq.collect_input_stats(lin, (x,), None)
-        h_trace = float(torch.diag(gq.H).sum())
-        qm, err = gq.quantize()
-        cases.append(dict(out_f=out_f, in_f=in_f, bits=bits, groupsize=gs, actorder=act, blocksize=bs, w=w, xs=xs, h_trace=h_trace,
-                          quant_weight=qm.quant_weight.clone(), scales=qm.scales.clone(), zeros=qm.zeros.clone(), error=err))
-    return cases
-
-
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.save(golden_quant(), os.path.join(OUT, "quant_cases.pt"))
     torch.save(golden_ops(), os.path.join(OUT, "ops.pt"))
-    torch.save(golden_gptq(), os.path.join(OUT, "gptq_cases.pt"))
     golden_model(torch.float32, "f32")
     golden_model(torch.bfloat16, "bf16")
     golden_dense_model()
