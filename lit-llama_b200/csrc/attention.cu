@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
                              __nv_bfloat16* __restrict__ v_cache, const float* __restrict__ rope,
                              const int64_t* __restrict__ input_pos, const int32_t* __restrict__ ring_start,
                              __nv_bfloat16* __restrict__ y, float* __restrict__ work, int* __restrict__ tickets,
-                             int n_head, int S, int block_size, int n_split, unsigned long long* tl, int pre_tiles) {
+                             int n_head, int S, int block_size, int n_split, unsigned long long* tl, int pre_tiles,
+                             int smem_merge) {
   constexpr int HS = 128;
   extern __shared__ __align__(128) uint8_t fsm[];
   float* sm_acc = reinterpret_cast<float*>(fsm + 4 * FD_SUB_BYTES);                // [FD_WARPS][HS]
@@ -448,26 +449,49 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   if (threadIdx.x == 0) tl_max(tl, 2);
   __syncwarp();
   if (threadIdx.x == 0) tl_max(tl, 3);
-  // ---- merge the 32 (warp, key group) partials of the CTA through shared memory: the K / V ring is idle now (every
-  // requested sub-tile has been consumed behind a __syncthreads), so its first 16 KB hold the partial rows.  One warp
-  // turns the 32 running maxima into weights, 128 threads add.  (Round 1 merged the key groups with 36 shuffles per
-  // warp first: 0.8-1.3 us of a 4-8 us kernel, tools/diag.py timeline.)
+  // ---- merge the 32 (warp, key group) partials of the CTA.  smem_merge: every group leaves its row in shared memory (the
+  // K / V ring is idle now: every requested sub-tile has been consumed behind a __syncthreads), one warp turns the 32
+  // running maxima into weights, 128 threads add.  Otherwise: the 4 key groups of a warp merge with shuffles first
+  // (36 per warp), then the 8 warps through shared memory.  A/B on one box: tools/env_sweep.sh B2L_ATTN_SMEM_MERGE=0/1.
   float* part = reinterpret_cast<float*>(fsm);                 // [32][HS]
   float* pm = part + 32 * HS;                                  // [32] running max, [32] sum, [32] weight, M, Ls
   float* pl = pm + 32, *pw = pl + 32;
-  {
+  const int n_part = smem_merge ? 32 : FD_WARPS;
+  if (smem_merge) {
     const int g = warp * 4 + grp;
     float4* dst = reinterpret_cast<float4*>(part + g * HS + d0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
     if (sub == 0) { pm[g] = m; pl[g] = l; }
+  } else {
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {   // lanes with the same `sub` hold the same dims
+      const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+      const float lo = __shfl_xor_sync(0xffffffffu, l, off);
+      const float mn = fmaxf(m, mo);
+      const float ca = (m == -INFINITY) ? 0.f : __expf(m - mn);
+      const float cb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+      l = l * ca + lo * cb;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float ao = __shfl_xor_sync(0xffffffffu, acc[i], off);
+        acc[i] = acc[i] * ca + ao * cb;
+      }
+      m = mn;
+    }
+    if (lane == 0) { pm[warp] = m; pl[warp] = l; }
+    if (grp == 0) {
+      float4* dst = reinterpret_cast<float4*>(part + warp * HS + d0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    }
   }
   __syncthreads();
   if (warp == 0) {
-    const float mi = pm[lane];
+    const float mi = lane < n_part ? pm[lane] : -INFINITY;
     const float Mx = warp_max(mi);
     const float wi = (mi == -INFINITY) ? 0.f : __expf(mi - Mx);
-    const float Lx = warp_sum(pl[lane] * wi);
+    const float Lx = warp_sum(lane < n_part ? pl[lane] * wi : 0.f);
     pw[lane] = wi;
     if (lane == 0) { pw[32] = Mx; pw[33] = Lx; }
   }
@@ -478,7 +502,7 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   float a = 0.f;
   if (writer) {
 #pragma unroll 8
-    for (int g = 0; g < 32; ++g) a = fmaf(part[g * HS + d], pw[g], a);
+    for (int g = 0; g < n_part; ++g) a = fmaf(part[g * HS + d], pw[g], a);
   }
   stamp();
   if (n_active == 1) {  // nothing to merge
@@ -802,11 +826,13 @@ extern "C" int b2l_attention(void* qkv, void* k_cache, void* v_cache, const void
     static DynSmemCache smem_cache;
     // B2L_ATTN_PRE (read once): sub-tiles requested before griddepcontrol.wait, 1 (default) or 2
     static const int env_pre = [] { const char* e = getenv("B2L_ATTN_PRE"); return e ? atoi(e) : 1; }();
+    // B2L_ATTN_SMEM_MERGE (read once): 1 = all 32 key groups merge through shared memory, 0 = shuffles inside a warp first
+    static const int env_smem_merge = [] { const char* e = getenv("B2L_ATTN_SMEM_MERGE"); return e ? atoi(e) : 1; }();
     if (int rc = ensure_dyn_smem(attn_decode_fused_kernel, FD_SMEM_BYTES, smem_cache)) return rc;
     LaunchCfg lc(dim3(B * n_head, n_split), dim3(FD_WARPS * 32), FD_SMEM_BYTES, st, (flags & B2L_F_PDL) != 0);
     B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, attn_decode_fused_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_cache,
                                 (__nv_bfloat16*)v_cache, (const float*)rope, input_pos, ring_start, (__nv_bfloat16*)y,
-                                (float*)work, tickets, n_head, S, block_size, n_split, (unsigned long long*)g_attn_timeline, env_pre));
+                                (float*)work, tickets, n_head, S, block_size, n_split, (unsigned long long*)g_attn_timeline, env_pre, env_smem_merge));
     return 0;
   }
   int rt = head_size / 2 < 32 ? 32 : head_size / 2;
