@@ -452,7 +452,8 @@ __global__ void __launch_bounds__(FD_WARPS * 32)
   // ---- merge the 32 (warp, key group) partials of the CTA.  smem_merge: every group leaves its row in shared memory (the
   // K / V ring is idle now: every requested sub-tile has been consumed behind a __syncthreads), one warp turns the 32
   // running maxima into weights, 128 threads add.  Otherwise: the 4 key groups of a warp merge with shuffles first
-  // (36 per warp), then the 8 warps through shared memory.  A/B on one box: tools/env_sweep.sh B2L_ATTN_SMEM_MERGE=0/1.
+  // (36 per warp), then the 8 warps through shared memory -- the default: measured 1.1 % faster per token at position
+  // 1030 on the same box (tools/env_sweep.sh "B2L_ATTN_SMEM_MERGE=0 B2L_ATTN_SMEM_MERGE=1").
   float* part = reinterpret_cast<float*>(fsm);                 // [32][HS]
   float* pm = part + 32 * HS;                                  // [32] running max, [32] sum, [32] weight, M, Ls
   float* pl = pm + 32, *pw = pl + 32;
@@ -827,7 +828,8 @@ extern "C" int b2l_attention(void* qkv, void* k_cache, void* v_cache, const void
     // B2L_ATTN_PRE (read once): sub-tiles requested before griddepcontrol.wait, 1 (default) or 2
     static const int env_pre = [] { const char* e = getenv("B2L_ATTN_PRE"); return e ? atoi(e) : 1; }();
     // B2L_ATTN_SMEM_MERGE (read once): 1 = all 32 key groups merge through shared memory, 0 = shuffles inside a warp first
-    static const int env_smem_merge = [] { const char* e = getenv("B2L_ATTN_SMEM_MERGE"); return e ? atoi(e) : 1; }();
+    // (default 0: same-box A/B at position 1030, 1125.7 vs 1138.8 us per 7B token -- the extra block barrier costs more than the shuffles)
+    static const int env_smem_merge = [] { const char* e = getenv("B2L_ATTN_SMEM_MERGE"); return e ? atoi(e) : 0; }();
     if (int rc = ensure_dyn_smem(attn_decode_fused_kernel, FD_SMEM_BYTES, smem_cache)) return rc;
     LaunchCfg lc(dim3(B * n_head, n_split), dim3(FD_WARPS * 32), FD_SMEM_BYTES, st, (flags & B2L_F_PDL) != 0);
     B2L_CUDA(cudaLaunchKernelEx(&lc.cfg, attn_decode_fused_kernel, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)k_cache,
