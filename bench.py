@@ -514,15 +514,18 @@ def main():
         if rank == 0:
             box["line"] = build_line(args, world, K, warm, t_dev, t_e2e, Ke, timed_pos, points, clk, t_q4, n_q4, q4_name, launches, lo)
         watchdog.start()
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import tp_bench
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import tp_bench
 
-            tp = {"7B": tp_bench.run_tp("7B", 96, 8, dev, rank, world)}
-            if world == 8:
-                tp["65B"] = tp_bench.run_tp("65B", 64, 8, dev, rank, world)
-        except Exception as e:  # noqa: BLE001 -- reported in the line, the replicas numbers stand
-            tp = {"error": f"{type(e).__name__}: {e}"[:300]}
+        tp = {}
+        # the model that NEEDS the split first (BASELINE.json configs[4]); every model in its own try: shapes are the same
+        # on every rank, so a failure is symmetric and the next model still runs
+        for name, steps in ([("65B", 64)] if world == 8 else []) + [("7B", 96)]:
+            try:
+                tp[name] = tp_bench.run_tp(name, steps, 8, dev, rank, world)
+            except Exception as e:  # noqa: BLE001 -- reported in the line, the replicas numbers stand
+                tp[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
         watchdog.cancel()
 
     if rank == 0:

@@ -61,3 +61,11 @@ def test_errors_are_reported_not_swallowed(L):
     assert lib.b2l_q4_tiled_bytes(130, 64) == 256 * 64 // 2  # rows padded to a multiple of 128
     assert lib.b2l_q4_tiled_bytes(128, 48) == 0              # K must be a multiple of 32
     assert lib.b2l_decode_step(None, None) == -1
+    # tensor-parallel exchange: buffer size = 2 epoch parities x world senders x n/2 words of 8 bytes; bad arguments say so
+    assert lib.b2l_tp_buffer_bytes(2, 4096) == 2 * 2 * 2048 * 8
+    assert lib.b2l_tp_buffer_bytes(9, 4096) == 0 and lib.b2l_tp_buffer_bytes(2, 4095) == 0
+    assert lib.b2l_tp_allreduce(None, None, None, 0, 0, None) == -1 and b"null pointer" in lib.b2l_last_error()
+    comm = L.TPComm()
+    comm.rank, comm.world, comm.max_elems = 3, 2, 4096
+    assert lib.b2l_tp_allreduce(C.byref(comm), C.c_void_p(16), C.c_void_p(16), 4096, 0, None) == -1
+    assert b"bad rank" in lib.b2l_last_error()
