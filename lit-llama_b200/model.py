@@ -7,9 +7,10 @@ Every forward runs hand-written sm_100a kernels (include/b2l.h); tensors must be
 bf16 - there is no CPU fallback.
 
 Two execution paths behind `LLaMA.forward`:
-  * decode (T == 1 with a KV cache, every Linear a tcgen05-capable gptq.int4 layer):
-    one C call enqueues the whole token (`b2l_decode_step`), replayed as a CUDA graph.
-  * everything else (prefill, no-cache forward, other Linear kinds): module by module.
+  * decode (T == 1 with a KV cache, every Linear a gptq.int4 layer with one (scale, zero) per row):
+    one C call enqueues the whole token (`b2l_decode_step`: int8-MMA GEMV kernels for batch 1, f16-MMA for 2..8 rows,
+    tcgen05 for 9..16), replayed as a CUDA graph.
+  * everything else (prefill on the tcgen05 GEMM, no-cache forward, other Linear kinds): module by module.
 """
 import ctypes as C
 import math
@@ -346,7 +347,7 @@ class LLaMA(nn.Module):
         self._kv_store: Optional[torch.Tensor] = None
         self._decode: Optional[_DecodeState] = None
         self._module_graph = None  # CUDA graph of the module-by-module decode step (non-fused Linear kinds)
-        self._fast_ok: Optional[bool] = None  # every Linear is a tcgen05-capable int4 layer (checked once)
+        self._fast_ok: Optional[bool] = None  # every Linear is a per-row gptq.int4 layer the fused step can run (checked once)
         self._fc12_cache = {}
 
     def _init_weights(self, module: nn.Module) -> None:
