@@ -200,7 +200,10 @@ def test_gemv_batch_prologue_epilogue(dev):
 
 
 @pytest.mark.parametrize("name,N,K", [("13B c_attn", 15360, 5120), ("13B mlp_proj", 5120, 13824), ("65B c_proj", 8192, 8192),
-                                      ("65B mlp_proj", 8192, 22016)])
+                                      ("65B mlp_proj", 8192, 22016),
+                                      # the shards of tensor-parallel decode (tp.py): 65B over 8 ranks, 7B over 4
+                                      ("65B/8 mlp_proj", 8192, 2752), ("65B/8 c_proj", 8192, 1024), ("65B/8 c_attn", 3072, 8192),
+                                      ("65B/8 lm_head", 4000, 8192), ("7B/4 c_proj", 4096, 1024)])
 def test_gemv_13b_65b_shapes(dev, name, N, K):
     """The other BASELINE model widths through the batch-1 kernel (K = 22016 exercises the wide-row prologue)."""
     from gpu_util import gemv_call, rand_q4, ref_linear, relerr, tile_i8
@@ -357,3 +360,31 @@ def test_int8_linear_vs_oracle(dev, N, K, M, outliers):
     assert (y - want).norm() / want.norm() < 2e-3, float((y - want).norm() / want.norm())
     torch.testing.assert_close(y, want, rtol=2 ** -6, atol=2e-2 * float(want.abs().max()) * 0.1 + 1e-3)
     assert (y - exact).norm() / exact.norm() < 3e-2  # the int8 scheme itself is ~1% accurate
+
+
+@pytest.mark.parametrize("n", [4096, 8192, 130])
+def test_tp_allreduce_single_rank_is_identity(dev, n):
+    """b2l_tp_allreduce with world = 1 (no peers): the multi-CTA indexing, the in-place path and the epoch words that
+    advance in device memory -- the sum of one row is that row.  The peer exchange itself needs 2 GPUs
+    (tests/test_gpu_persistent.py::test_tensor_parallel_matches_single_gpu)."""
+    import ctypes as C
+
+    from lit_llama_b200 import _lib as L
+
+    lib = L.lib()
+    buf = torch.zeros(lib.b2l_tp_buffer_bytes(1, 8192), dtype=torch.uint8, device=dev)
+    words = torch.zeros(32, dtype=torch.int32, device=dev)
+    comm = L.TPComm()
+    comm.peer_buf[0] = buf.data_ptr()
+    comm.rank, comm.world, comm.max_elems = 0, 1, 8192
+    comm.epoch, comm.status = words.data_ptr(), words.data_ptr() + 64
+    x = torch.randn(n, device=dev).bfloat16()
+    y = torch.empty_like(x)
+    for step in range(3):
+        L.check(lib.b2l_tp_allreduce(C.byref(comm), x.data_ptr(), y.data_ptr(), n, 0, L.stream_ptr()), "b2l_tp_allreduce")
+        assert torch.equal(x, y)
+    z = x.clone()
+    L.check(lib.b2l_tp_allreduce(C.byref(comm), z.data_ptr(), z.data_ptr(), n, L.F_PDL, L.stream_ptr()), "b2l_tp_allreduce")  # in place
+    assert torch.equal(x, z)
+    n_ctas = (n // 2 + 511) // 512
+    assert words[:n_ctas].tolist() == [4] * n_ctas and int(words[16]) == 0
