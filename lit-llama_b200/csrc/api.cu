@@ -91,7 +91,6 @@ static std::vector<PfWindow> prefetch_windows(const b2l_decode_args* d) {
   if (D == 0) return out;
   std::vector<size_t> start(n + 1, 0);
   for (size_t j = 0; j < n; ++j) start[j + 1] = start[j] + ops[j].second;
-  const size_t total = start[n];
   for (size_t j = 0; j < n; ++j) {
     size_t lo = std::max(start[j] + D, start[j + 1]), hi = start[j + 1] + D;   // may run past `total`: wraps to the next token
     int sg = 0;
@@ -112,7 +111,6 @@ static std::vector<PfWindow> prefetch_windows(const b2l_decode_args* d) {
       base = op_hi;
       ++k;
     }
-    (void)total;
   }
   return out;
 }
