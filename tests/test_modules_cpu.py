@@ -180,3 +180,41 @@ def test_empty_init_on_device_and_lazy_load(tmp_path):
         m.load_state_dict(ck)
     for k, v in m.state_dict().items():
         assert torch.equal(v, sd[k]) and v.stride() == sd[k].stride(), k
+
+
+def test_weight_changes_bump_the_generation_and_compact_refuses_what_it_cannot_serve():
+    """Host logic behind two round-2 features, no kernels involved: (1) load_state_dict / pack_weight / .to() bump the
+    generation counter that invalidates baked decode states (lit_llama_b200/model.py); (2) compact() /
+    release_reference_layout() refuse models and layers the batch-1 decode tiling cannot represent instead of
+    freeing their only copy."""
+    from lit_llama_b200.quantization import WEIGHTS_GENERATION
+
+    cfg = dict(block_size=16, vocab_size=32, n_layer=1, n_head=2, n_embd=64)
+    with quantization("gptq.int4"):
+        m = P.LLaMA(P.LLaMAConfig(**cfg))
+    g0 = WEIGHTS_GENERATION[0]
+    m.load_state_dict(m.state_dict())
+    g1 = WEIGHTS_GENERATION[0]
+    assert g1 > g0
+    lin = m.transformer.h[0].attn.c_proj
+    lin.scales.fill_(1.0); lin.zeros.fill_(8.0)
+    lin.pack_weight(torch.zeros(64, 64))
+    assert WEIGHTS_GENERATION[0] > g1
+    g2 = WEIGHTS_GENERATION[0]
+    m.to(torch.bfloat16)
+    assert WEIGHTS_GENERATION[0] > g2
+    # a dense model has nothing to compact
+    dense = P.LLaMA(P.LLaMAConfig(**cfg))
+    with pytest.raises(RuntimeError):
+        dense.compact()
+    # grouped scales (gptq with groupsize) and int8 levels are outside the batch-1 tiling: the buffer stays
+    grouped = P.ColBlockQuantizedLinear(128, 32, bias=False, bits=4, tile_cols=64)
+    with pytest.raises(RuntimeError):
+        grouped.release_reference_layout()
+    assert grouped.quant_weight.numel() == 32 * 64 and not grouped._released
+    q8 = P.ColBlockQuantizedLinear(128, 32, bias=False, bits=8, tile_cols=-1)
+    with pytest.raises(RuntimeError):
+        q8.release_reference_layout()
+    # state_dict of an untouched module is the registered buffer itself (reference strides)
+    sd = grouped.state_dict()
+    assert sd["quant_weight"].stride() == (1, 32)
