@@ -132,7 +132,7 @@ def test_per_op_path_pdl_equals_plain_order(dev):
 
 
 def test_tensor_parallel_matches_single_gpu(dev):
-    """TPLLaMA on 2 GPUs (module path and the fused graph-replayed rank step) vs the single-GPU model: tools/tp_check.py
+    """TPLLaMA on 2 GPUs (module path and the fused graph-replayed rank step) vs the single-GPU model: tests/tp_check.py
     under torch.distributed.run.  Skipped on a one-GPU box."""
     import os
     import subprocess
@@ -142,6 +142,6 @@ def test_tensor_parallel_matches_single_gpu(dev):
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29517", os.path.join(root, "tools", "tp_check.py")], capture_output=True, text=True, timeout=600)
+                        "--master-port", "29517", os.path.join(root, "tests", "tp_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("OK") >= 2, r.stdout[-2000:]

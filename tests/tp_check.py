@@ -1,6 +1,6 @@
 """Tensor-parallel check on N GPUs of one node:
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/tp_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/tp_check.py
 
 TPLLaMA logits (prefill + decode) vs the single-GPU LLaMA on rank 0's GPU, for a head_size-32 model (module path) and a
 head_size-128 model (the fused per-rank decode step, CUDA-graph replayed with the NCCL all-reduces inside).  Exit code 1

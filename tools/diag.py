@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "ops", "model", "mma_rate", "mma_issuers", "grid_flag", "hmma_rate", "imma_rate", "consumer_rate", "bench_gemm", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline", "mega_timeline"]
+SECTIONS = ["generic", "tile", "tc_small", "tc_shapes", "tc_modes", "gemv", "mma_rate", "mma_issuers", "grid_flag", "hmma_rate", "imma_rate", "consumer_rate", "bench_gemm", "trace", "bench_layers", "bench_gemv", "bench_step", "bench_ctx", "bench_13b_b8", "bench_sizes", "batch_debug", "bench_step_int8", "timeline", "mega_timeline"]
 
 
 _DLIB = None
@@ -398,96 +398,6 @@ def sec_tc_modes():
     y, err = tc_call(L, x, qt, sc, z, N, K)
     torch.cuda.synchronize()
     print("fp32 scales:", err or f"relerr={relerr(y, ref_linear(x, lv, sc, z)):.3e}")
-
-
-def sec_ops():
-    import torch
-    import lit_llama_b200 as P
-    from lit_llama_b200.utils import quantization
-    from oracle import llama_oracle as O
-
-    dev = torch.device("cuda")
-    x = torch.randn(3, 5, 4096, device=dev).bfloat16()
-    n = P.RMSNorm(4096).to(dev).bfloat16()
-    n.scale.data = (1 + 0.1 * torch.randn(4096, device=dev)).bfloat16()
-    y = n(x)
-    want = O.rmsnorm(x.cpu(), n.scale.data.cpu())
-    print(f"rmsnorm: exact_frac={float((y.cpu() == want).float().mean()):.5f} relerr={relerr(y.cpu(), want):.2e}")
-    tab = O.rope_table(64, 128).to(dev)
-    xr = torch.randn(2, 9, 4, 128, device=dev).bfloat16()
-    yr = P.apply_rope(xr, tab)
-    wr = O.rope_apply(xr.cpu(), tab.cpu())
-    print(f"rope: exact_frac={float((yr.cpu() == wr).float().mean()):.5f}")
-
-
-def _tiny(dev, cfg, mode="gptq.int4", seed=1234):
-    import torch
-    import lit_llama_b200 as P
-    from lit_llama_b200.utils import quantization
-    from oracle import llama_oracle as O
-
-    sd = O.synth_state_dict(cfg["n_layer"], cfg["n_head"], cfg["n_embd"], cfg["vocab_size"], mode, dtype=torch.bfloat16, seed=seed)
-    prev = torch.get_default_dtype()
-    torch.set_default_dtype(torch.bfloat16)
-    try:
-        with torch.device(dev), quantization(mode):
-            model = P.LLaMA(P.LLaMAConfig(**cfg))
-    finally:
-        torch.set_default_dtype(prev)
-    model.load_state_dict(sd)
-    return model.eval(), O.OracleLLaMA.from_state_dict(sd, cfg["n_layer"], cfg["n_head"], cfg["block_size"], mode)
-
-
-def sec_model():
-    import torch
-    import lit_llama_b200 as P
-    from lit_llama_b200.utils import quantization
-    from oracle import llama_oracle as O
-
-    dev = torch.device("cuda")
-    cfg = dict(block_size=64, vocab_size=96, n_layer=2, n_head=4, n_embd=128)
-    gd = torch.load(os.path.join(ROOT, "tests/golden/tiny_int4_bf16.pt"), weights_only=False)
-    for graph_after in (0, 2):
-        model, orc = _tiny(dev, cfg)
-        model.graph_after = graph_after
-        prompt = gd["prompt"]
-        S = 16
-        with torch.no_grad():
-            got = [model(prompt.view(1, -1).to(dev), S, torch.arange(7, device=dev))]
-            for i, t in enumerate(gd["steps_tokens"] + [4, 9, 60]):
-                got.append(model(torch.tensor([[t]], device=dev), S, torch.tensor([7 + i], device=dev)))
-        torch.cuda.synchronize()
-        for i, (g_, w_) in enumerate(zip(got, gd["steps_logits"])):
-            d = (g_.float().cpu() - w_.float())
-            print(f"model graph_after={graph_after} step {i}: max_abs={float(d.abs().max()):.4f} relerr={relerr(g_.cpu(), w_):.3e}")
-        k0 = model.kv_caches[0][0].float().cpu()
-        print(f"   kv0_k relerr={relerr(k0[:, :, :10], gd['kv0_k'][:, :, :10]):.3e}")
-    # generate: greedy tokens vs golden, roll branch
-    model, orc = _tiny(dev, cfg)
-    with torch.no_grad():
-        y = P.generate(model, gd["prompt"].to(torch.int32).to(dev), 12, top_k=1)
-    print("generate greedy match:", bool(torch.equal(y.cpu(), gd["gen_greedy"])), y.cpu().tolist(), gd["gen_greedy"].tolist())
-    model.reset_cache()
-    torch.manual_seed(99)
-    with torch.no_grad():
-        y = P.generate(model, gd["prompt"].to(torch.int32).to(dev), 12, max_seq_length=10, top_k=4)
-    print("generate roll len:", y.shape, y.cpu().tolist(), "golden(cpu rng)", gd["gen_roll"].tolist())
-    # roll-branch logits vs golden
-    model.reset_cache()
-    S2 = 8
-    with torch.no_grad():
-        got = [model(gd["prompt"].view(1, -1).to(dev), S2, torch.arange(7, device=dev))[:, -1]]
-        for i, t in enumerate(gd["roll_tokens"]):
-            got.append(model(torch.tensor([[t]], device=dev), S2, torch.tensor([7 + i], device=dev))[:, -1])
-    for i, (g_, w_) in enumerate(zip(got, gd["roll_logits"])):
-        print(f"roll step {i}: max_abs={float((g_.float().cpu() - w_.float()).abs().max()):.4f} relerr={relerr(g_.cpu(), w_):.3e}")
-    kl = model.logical_kv_caches()[1][0]
-    print(f"   roll kv1_k relerr={relerr(kl.cpu(), gd['roll_kv1_k']):.3e}")
-    # no-cache forward
-    model.reset_cache()
-    with torch.no_grad():
-        lg = model(gd["prompt"].view(1, -1).to(dev))
-    print(f"nocache relerr={relerr(lg.cpu(), gd['nocache_logits']):.3e}")
 
 
 def _time(fn, iters=20, warm=3):
